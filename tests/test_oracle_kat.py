@@ -1,0 +1,141 @@
+"""Pins the CPU checker (oracle/) against every known-answer test the reference holds for
+the hot path and its doorstep.  CPU only."""
+import numpy as np
+import pytest
+
+JOHNSON = "6 4\n2 3\n2 2 2 2 2 2\n3 3 3 3\n1 3\n1 2\n2 4\n1 4\n2 3\n3 4\n1 2 4\n2 3 5\n1 5 6\n3 4 6\n"
+
+
+# ---- src/sparse.rs:548-647
+ALIST_REG = "12 4\n1 3\n1 1 1 1 1 1 1 1 1 1 1 1\n3 3 3 3\n1\n2\n3\n4\n1\n2\n3\n4\n1\n2\n3\n4\n1 5 9\n2 6 10\n3 7 11\n4 8 12\n"
+ALIST_IRR = "12 4\n1 3\n1 1 1 1 1 1 1 1 1 1 0 0\n3 3 2 2\n1\n2\n3\n4\n1\n2\n3\n4\n1\n2\n0\n0\n1 5 9\n2 6 10\n3 7 0\n4 8 0\n"
+ALIST_IRR_NOPAD = "12 4\n1 3\n1 1 1 1 1 1 1 1 1 1 0 0\n3 3 2 2\n1\n2\n3\n4\n1\n2\n3\n4\n1\n2\n\n\n1 5 9\n2 6 10\n3 7\n4 8\n"
+
+
+def test_alist_regular(oracle):
+    assert oracle.alist_roundtrip(ALIST_REG) == ALIST_REG
+
+
+def test_alist_irregular(oracle):
+    assert oracle.alist_roundtrip(ALIST_IRR) == ALIST_IRR
+    assert oracle.alist_roundtrip(ALIST_IRR, padding=False) == ALIST_IRR_NOPAD
+    assert oracle.alist_roundtrip(ALIST_IRR_NOPAD) == ALIST_IRR
+    assert oracle.alist_roundtrip(ALIST_IRR_NOPAD, padding=False) == ALIST_IRR_NOPAD
+
+
+def test_alist_errors(oracle):
+    assert oracle.alist_roundtrip("") is None
+    assert oracle.alist_roundtrip("12") is None
+    assert oracle.alist_roundtrip("x 4\n") is None
+    # str::split('\n') yields a trailing empty line, which the parser accepts as an empty column
+    assert oracle.alist_roundtrip("3 2\n1 1\n1 1 1\n1 1\n1\n2\n") == "3 2\n1 1\n1 1 0\n1 1\n1\n2\n0\n1\n2\n"
+    assert oracle.alist_roundtrip("3 2\n1 1\n1 1 1\n1 1\n1\n2") is None        # missing column line
+    assert oracle.alist_roundtrip("3 2\n1 1\n1 1 1\n1 1\n1\nfoo\n1\n") is None  # not a number
+
+
+# ---- src/decoder/flooding.rs:138-189 (Johnson example 2.5 / 2.23, Phif64)
+def _to_llrs(bits):
+    return np.array([1.3863 if b == 0 else -1.3863 for b in bits])
+
+
+def test_flooding_phif64_no_errors(oracle):
+    dec = oracle.decoder(JOHNSON, "Phif64")
+    cw = [0, 0, 1, 0, 1, 1]
+    out, it = dec.decode(_to_llrs(cw), 100)
+    assert out.tolist() == cw and it == 0
+
+
+def test_flooding_phif64_single_error(oracle):
+    dec = oracle.decoder(JOHNSON, "Phif64")
+    good = [0, 0, 1, 0, 1, 1]
+    for j in range(6):
+        bad = list(good)
+        bad[j] ^= 1
+        out, it = dec.decode(_to_llrs(bad), 100)
+        assert out.tolist() == good and it == 1
+
+
+def test_johnson_alist_is_the_reference_matrix(oracle):
+    # rows [0,1,3] [1,2,4] [0,4,5] [2,3,5]  (flooding.rs:146-149)
+    assert oracle.alist_roundtrip(JOHNSON) == JOHNSON
+
+
+# ---- src/encoder.rs:128-197
+ENC_DENSE = ("12 4\n3 9 \n3 3 3 3 3 3 3 3 3 3 3 3 \n9 9 9 9 \n1 2 3 \n1 3 4 \n2 3 4 \n2 3 4 \n1 2 4 \n1 2 3 \n1 3 4 \n1 2 4 \n"
+             "1 2 3 \n2 3 4 \n1 2 4 \n1 3 4 \n1 2 5 6 7 8 9 11 12 \n1 3 4 5 6 8 9 10 11 \n1 2 3 4 6 7 9 10 12 \n2 3 4 5 7 8 10 11 12 \n")
+ENC_STAIR = "5 3\n2 4\n2 2 2 2 1\n2 4 4\n1 3\n2 3\n1 2\n2 3\n3\n1 3\n2 3 4\n1 2 4 5\n"
+
+
+def test_encoder_dense(oracle):
+    enc = oracle.encoder(ENC_DENSE)
+    assert not enc.is_staircase
+    assert enc.encode([1, 0, 1, 1, 0, 0, 1, 0], 12).tolist() == [1, 0, 1, 1, 0, 0, 1, 0, 1, 0, 0, 1]
+    assert enc.encode([0, 1, 0, 0, 1, 1, 1, 0], 12).tolist() == [0, 1, 0, 0, 1, 1, 1, 0, 1, 0, 1, 0]
+
+
+def test_encoder_staircase(oracle):
+    enc = oracle.encoder(ENC_STAIR)
+    assert enc.is_staircase
+    assert enc.encode([1, 0], 5).tolist() == [1, 0, 1, 1, 0]
+    assert enc.encode([0, 1], 5).tolist() == [0, 1, 0, 1, 0]
+
+
+def test_staircase_detector(oracle):
+    # src/encoder/staircase.rs:30-46: 3x5, ones added one at a time
+    def alist(entries):
+        cols = [[] for _ in range(5)]
+        for r, c in entries:
+            cols[c].append(r + 1)
+        lines = ["5 3", "3 3", "0 0 0 0 0", "0 0 0"] + [" ".join(map(str, c)) if c else "0" for c in cols] + ["0"] * 3
+        return "\n".join(lines) + "\n"
+    seq = [(0, 2), (1, 2), (1, 3), (2, 3), (2, 4)]
+    for i in range(1, 5):
+        # not yet a staircase: H1 singular -> encoder ctor fails, or dense path taken
+        try:
+            assert not oracle.encoder(alist(seq[:i])).is_staircase
+        except ValueError:
+            pass
+    assert oracle.encoder(alist(seq)).is_staircase
+    try:   # one extra one in the first row: not a staircase any more (and H1 is singular here)
+        assert not oracle.encoder(alist(seq + [(0, 3)])).is_staircase
+    except ValueError:
+        pass
+
+
+# ---- src/simulation/puncturing.rs:118-129 (through the C-API shaped entry points)
+def test_puncturing_kat(oracle):
+    # depuncture: zeros inserted for punctured blocks.  A 10x... identity-free way to see it:
+    # build a decoder whose pre-check passes immediately so the output is the hard decision
+    # of the depunctured LLRs (0.0 -> bit 1).
+    n = 10
+    alist = f"{n} 1\n1 2\n" + " ".join(["0"] * n) + "\n0\n" + "0\n" * n + "0\n"
+    dec = oracle.decoder(alist, "Phif64", "1,1,0,1,0")
+    out, it = dec.decode(np.array([1.0, 2.0, 3.0, 4.0, 5.0, 6.0]), 5)
+    assert it == 0
+    assert out.tolist() == [0, 0, 0, 0, 1, 1, 0, 0, 1, 1]
+    # bad patterns -> ctor NULL (src/cli/ber.rs:219-229)
+    for bad in ("1,1,2", "1, 0", "a", "1,,0"):
+        with pytest.raises(ValueError):
+            oracle.decoder(alist, "Phif64", bad)
+
+
+def test_puncture_encoder(oracle):
+    enc = oracle.encoder(ENC_DENSE, "1,1,0")
+    assert enc.encode([1, 0, 1, 1, 0, 0, 1, 0], 8).tolist() == [1, 0, 1, 1, 0, 0, 1, 0]
+
+
+# ---- src/simulation/modulation.rs:294-309 + ber.rs:300-302 via sigma
+def test_noise_sigma(oracle):
+    # Es/N0 = rate*bps*10^(EbN0/10); sigma = sqrt(0.5/EsN0)
+    assert abs(oracle.lib.ldpc_oracle_noise_sigma(0.5, 1.0, 0.0) - 1.0) < 1e-12
+    assert abs(oracle.lib.ldpc_oracle_noise_sigma(1.0, 1.0, 10.0) - np.sqrt(0.05)) < 1e-12
+
+
+# ---- factory.rs:240-277
+def test_implementation_names(oracle):
+    names = oracle.implementations()
+    assert len(names) == 36 and len(set(names)) == 36
+    assert names[0] == "Phif64" and "HLAminstari8PartialHardLimit" in names
+    assert sum(n.startswith("HL") for n in names) == 12
+    with pytest.raises(ValueError):
+        oracle.decoder(JOHNSON, "phif64")      # case-sensitive
