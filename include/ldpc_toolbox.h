@@ -1,0 +1,115 @@
+/* include/ldpc_toolbox.h — C ABI of the B200-native LDPC decoder / BER engine.
+ *
+ * Part 1 re-declares, with identical names, argument order and types, the nine entry points of
+ * the reference's FFI (reference include/ldpc_toolbox.h:11-30, implemented in
+ * src/c_api/decoder.rs:78-137 and src/c_api/encoder.rs:54-97), so a program linked against the
+ * reference's libldpc_toolbox.{so,a} links against this library unchanged.
+ *
+ * Part 2 is additive: batched decode (the native shape of the GPU path), device-pointer
+ * variants, an on-device BER engine and introspection.  Nothing in part 1 changes meaning.
+ *
+ * Error behaviour: constructors return NULL on any error, as the reference does
+ * (c_api/decoder.rs:84-87).  Where the reference panics across the FFI (length mismatches,
+ * flooding.rs:56, c_api/decoder.rs:51,:61, c_api/encoder.rs:44,:48) this library returns -2
+ * from decode / leaves the encoder output untouched, and never reads or writes out of bounds.
+ * ldpc_toolbox_last_error() describes the last failure on the calling thread.
+ *
+ * There is no CPU fallback: without a CUDA device every constructor returns NULL.
+ */
+#ifndef LDPC_TOOLBOX_H_
+#define LDPC_TOOLBOX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Part 1 — the reference's ABI
+ * ------------------------------------------------------------------------------------------ */
+
+/* reference src/c_api/decoder.rs:78-88.  `implementation` is one of the 36 names of
+ * src/decoder/factory.rs:240-277 (case-sensitive); `puncturing` is "" or e.g. "1,1,1,1,0". */
+void *ldpc_toolbox_decoder_ctor(const char *alist_file_path, const char *implementation,
+                                const char *puncturing);
+/* reference src/c_api/decoder.rs:90-102 */
+void *ldpc_toolbox_decoder_ctor_alist_string(const char *alist, const char *implementation,
+                                             const char *puncturing);
+/* reference src/c_api/decoder.rs:104-107 */
+void ldpc_toolbox_decoder_dtor(void *decoder);
+/* reference src/c_api/decoder.rs:109-122.  Returns the iteration count (>= 0) on success and -1
+ * on decoding failure; `output` receives the first output_len hard bits (one 0/1 per byte) in
+ * both cases.  -2: argument error / a check node the min* rules cannot process. */
+int32_t ldpc_toolbox_decoder_decode_f64(void *decoder, uint8_t *output, size_t output_len,
+                                        const double *llrs, size_t llrs_len,
+                                        uint32_t max_iterations);
+/* reference src/c_api/decoder.rs:124-137 (f32 is widened to f64, :69-72) */
+int32_t ldpc_toolbox_decoder_decode_f32(void *decoder, uint8_t *output, size_t output_len,
+                                        const float *llrs, size_t llrs_len,
+                                        uint32_t max_iterations);
+
+/* reference src/c_api/encoder.rs:54-65 */
+void *ldpc_toolbox_encoder_ctor(const char *alist_file_path, const char *puncturing);
+/* reference src/c_api/encoder.rs:67-77 */
+void *ldpc_toolbox_encoder_ctor_alist_string(const char *alist, const char *puncturing);
+/* reference src/c_api/encoder.rs:79-82 */
+void ldpc_toolbox_encoder_dtor(void *encoder);
+/* reference src/c_api/encoder.rs:84-97.  input bytes equal to 1 are ones, anything else zero;
+ * output_len must equal the (punctured) codeword length. */
+void ldpc_toolbox_encoder_encode(void *encoder, uint8_t *output, size_t output_len,
+                                 const uint8_t *input, size_t input_len);
+
+/* ------------------------------------------------------------------------------------------
+ * Part 2 — additive entry points
+ * ------------------------------------------------------------------------------------------ */
+
+const char *ldpc_toolbox_last_error(void);
+
+/* Constructor with placement options: CUDA device ordinal (-1 = current) and the maximum number
+ * of 128-frame tiles processed per kernel launch (0 = automatic). */
+void *ldpc_toolbox_decoder_ctor_ex(const char *alist, int alist_is_path, const char *implementation,
+                                   const char *puncturing, int device, int max_tiles);
+
+/* Batched decode(llrs, max_iterations) on host buffers: frame f reads llrs[f*llrs_len ..] and
+ * writes output[f*output_stride .. +output_len] and iterations[f] (>= 0, -1 failure, -2 error).
+ * Returns 0, or -2 on an argument / CUDA error (nothing is written). */
+int32_t ldpc_toolbox_decoder_decode_batch_f32(void *decoder, uint8_t *output, size_t output_len,
+                                              size_t output_stride, const float *llrs,
+                                              size_t llrs_len, size_t nframes,
+                                              uint32_t max_iterations, int32_t *iterations);
+int32_t ldpc_toolbox_decoder_decode_batch_f64(void *decoder, uint8_t *output, size_t output_len,
+                                              size_t output_stride, const double *llrs,
+                                              size_t llrs_len, size_t nframes,
+                                              uint32_t max_iterations, int32_t *iterations);
+/* Same, with every buffer in device memory of the decoder's GPU; asynchronous on `cuda_stream`
+ * (a cudaStream_t; NULL = the legacy default stream). */
+int32_t ldpc_toolbox_decoder_decode_batch_device_f32(void *decoder, uint8_t *d_output,
+                                                     size_t output_len, size_t output_stride,
+                                                     const float *d_llrs, size_t llrs_len,
+                                                     size_t nframes, uint32_t max_iterations,
+                                                     int32_t *d_iterations, void *cuda_stream);
+int32_t ldpc_toolbox_decoder_decode_batch_device_f64(void *decoder, uint8_t *d_output,
+                                                     size_t output_len, size_t output_stride,
+                                                     const double *d_llrs, size_t llrs_len,
+                                                     size_t nframes, uint32_t max_iterations,
+                                                     int32_t *d_iterations, void *cuda_stream);
+
+/* Introspection */
+size_t ldpc_toolbox_decoder_codeword_len(void *decoder);   /* n (columns of H) */
+size_t ldpc_toolbox_decoder_info_len(void *decoder);       /* k = n - rows of H */
+size_t ldpc_toolbox_decoder_num_edges(void *decoder);      /* ones in H */
+size_t ldpc_toolbox_decoder_llrs_len(void *decoder);       /* expected llrs_len (after puncturing) */
+/* device time in ms of the stages of the last processed chunk: [ingest, decode, emit];
+ * returns the number of kernels launched by this handle so far */
+int64_t ldpc_toolbox_decoder_last_timing(void *decoder, float *ms3);
+
+int32_t ldpc_toolbox_num_implementations(void);
+const char *ldpc_toolbox_implementation_name(int32_t index);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* LDPC_TOOLBOX_H_ */

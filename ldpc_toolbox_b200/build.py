@@ -1,0 +1,86 @@
+"""Builds the CUDA extension in-tree: ldpc_toolbox_b200/_build/libldpc_toolbox.so (sm_100a only).
+
+nvcc cross-compiles without a GPU; the resulting .so travels with the repo snapshot to the GPU
+box.  Nothing here falls back to a CPU implementation: if the build or the load fails, importing
+the C-ABI raises.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT_DIR, "libldpc_toolbox.so")
+
+CU_SOURCES = ["capi.cu", "decoder.cu", "flood_i8.cu", "ingest.cu"]
+CPP_SOURCES = ["host.cpp"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O3,-Wall", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    cand = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found")
+    return cand
+
+
+def _sources():
+    names = CU_SOURCES + CPP_SOURCES
+    extra = [f for f in sorted(os.listdir(CSRC)) if f.endswith((".hpp", ".cuh", ".h"))]
+    return names, extra
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    names, extra = _sources()
+    for f in names + extra:
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    h.update(open(os.path.join(HERE, "..", "include", "ldpc_toolbox.h"), "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OUT_DIR, exist_ok=True)
+    stamp = os.path.join(OUT_DIR, "stamp.txt")
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return LIB
+    nvcc = _nvcc()
+    objs = []
+    log = []
+    # the image exports CXX=/opt/gcc/bin/g++ (a wrapper); nvcc must use the system host compiler
+    ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+    for src in CU_SOURCES + CPP_SOURCES:
+        obj = os.path.join(OUT_DIR, src.rsplit(".", 1)[0] + ".o")
+        cmd = [nvcc] + ccbin + NVCC_FLAGS + ["-x", "cu" if src.endswith(".cu") else "c++", "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            sys.stderr.write(log[-1])
+            raise RuntimeError(f"nvcc failed on {src}")
+        objs.append(obj)
+    cmd = [nvcc] + ccbin + ["-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        sys.stderr.write(log[-1])
+        raise RuntimeError("link failed")
+    open(os.path.join(OUT_DIR, "build.log"), "w").write("\n".join(log))
+    open(stamp, "w").write(dig)
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

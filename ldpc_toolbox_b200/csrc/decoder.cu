@@ -1,0 +1,291 @@
+// ldpc_toolbox_b200/csrc/decoder.cu — host-side decoder object: owns the uploaded graph layout and
+// the per-tile HBM workspace, and drives ingest -> BP kernel -> emit on one CUDA stream.
+//
+// Mirrors DecoderImplementation::build_decoder (reference src/decoder/factory.rs:202-208) and the
+// decode wrapper of the C API (reference src/c_api/decoder.rs:50-72).
+#include "decoder.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+#include "decoder_impl.hpp"
+
+namespace ldpc {
+
+namespace {
+thread_local std::string g_last_error;
+}
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const std::string& last_error() { return g_last_error; }
+
+namespace {
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t count = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; count = 0; }
+    bool ensure(size_t c) {
+        if (c <= count) return true;
+        release();
+        if (cudaMalloc(&p, c * sizeof(T)) != cudaSuccess) {
+            cudaGetLastError();
+            set_last_error("cudaMalloc of " + std::to_string(c * sizeof(T)) + " bytes failed");
+            return false;
+        }
+        count = c;
+        return true;
+    }
+    bool upload(const std::vector<T>& h) {
+        if (!ensure(std::max<size_t>(h.size(), 1))) return false;
+        if (!h.empty() && cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_last_error("graph upload failed");
+            return false;
+        }
+        return true;
+    }
+};
+
+class GpuDecoder final : public LdpcDecoder {
+public:
+    GpuDecoder(const DecoderImplementation& impl, const Graph& g) : impl_(impl), g_(g) {}
+    ~GpuDecoder() override {
+        if (stream_) cudaStreamDestroy(stream_);
+        for (auto& e : ev_) if (e) cudaEventDestroy(e);
+    }
+
+    bool init(const Puncturer* punct, const DecoderOptions& opt) {
+        if (opt.device >= 0) LDPC_CUDA_CHECK(cudaSetDevice(opt.device));
+        LDPC_CUDA_CHECK(cudaGetDevice(&device_));
+        cudaDeviceProp prop;
+        LDPC_CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
+        sm_count_ = prop.multiProcessorCount;
+        if (punct) punct_ = std::make_unique<Puncturer>(*punct);
+        expected_len_ = (size_t)g_.n;
+        if (punct_) {
+            // reference: depuncture() expands blocks of llrs_len/num_trues; the result must be n
+            if (g_.n % (int)punct_->pattern.size() != 0) { set_last_error("codeword size not divisible by puncturing pattern length"); return false; }
+            expected_len_ = (size_t)g_.n / punct_->pattern.size() * punct_->num_trues;
+            std::vector<int> map;
+            if (!punct_->depuncture_map(expected_len_, (size_t)g_.n, &map)) { set_last_error("bad puncturing pattern"); return false; }
+            if (!d_src_map_.upload(map)) return false;
+        }
+        // rows the min* rules cannot process: the reference panics on them during the first
+        // iteration (arithmetic.rs:744-745, :952, :971); here such frames report -2.
+        panics_ = false;
+        if (impl_.rule == Rule::Minstarapprox || impl_.rule == Rule::Aminstar) {
+            for (int r = 0; r < g_.m; ++r) {
+                int d = g_.row_ptr[(size_t)r + 1] - g_.row_ptr[(size_t)r];
+                if (d == 1 || (d == 0 && impl_.rule == Rule::Aminstar)) panics_ = true;
+            }
+        }
+        if (impl_.dtype == Dtype::I8 && impl_.schedule == Schedule::Flooding && g_.max_row_deg > flood_i8_max_row_degree()) {
+            set_last_error("row degree above the supported maximum of " + std::to_string(flood_i8_max_row_degree()));
+            return false;
+        }
+        if (impl_.dtype != Dtype::I8 || impl_.schedule != Schedule::Flooding) {
+            set_last_error("decoder implementation " + impl_.name + " is not available in this build yet");
+            return false;
+        }
+        if (!d_row_ptr_.upload(g_.row_ptr) || !d_col_idx_.upload(g_.col_idx) || !d_col_ptr_.upload(g_.col_ptr) ||
+            !d_col_edge_.upload(g_.col_edge))
+            return false;
+        dg_.n = g_.n; dg_.m = g_.m; dg_.E = g_.E;
+        dg_.row_ptr = d_row_ptr_.p; dg_.col_idx = d_col_idx_.p; dg_.col_ptr = d_col_ptr_.p; dg_.col_edge = d_col_edge_.p;
+        LDPC_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        for (auto& e : ev_) LDPC_CUDA_CHECK(cudaEventCreate(&e));
+        max_tiles_opt_ = opt.max_tiles;
+        return true;
+    }
+
+    int n() const override { return g_.n; }
+    int k() const override { return g_.n - g_.m; }
+    int edges() const override { return g_.E; }
+    size_t expected_llrs_len() const override { return expected_len_; }
+    const BatchStats& stats() const override { return stats_; }
+
+    bool decode(const double* llrs, size_t llrs_len, size_t max_iterations, DecoderOutput* out) override {
+        out->codeword.assign((size_t)g_.n, 0);
+        int32_t it = 0;
+        uint32_t mi = (uint32_t)std::min<size_t>(max_iterations, 0x7fffffffu);
+        if (!decode_batch(llrs, true, llrs_len, 1, mi, out->codeword.data(), (size_t)g_.n, (size_t)g_.n, &it)) return false;
+        if (it == -2) { set_last_error("check node of degree < 2 with a min* rule (the reference panics)"); return false; }
+        out->success = it >= 0;
+        out->iterations = it >= 0 ? (size_t)it : max_iterations;
+        return true;
+    }
+
+    bool decode_batch(const void* llrs, bool is_f64, size_t llrs_len, size_t nframes, uint32_t max_iterations,
+                      uint8_t* out, size_t out_len, size_t out_stride, int32_t* iterations) override {
+        if (!check_args(llrs_len, out_len, out_stride)) return false;
+        if (nframes == 0) return true;
+        LDPC_CUDA_CHECK(cudaSetDevice(device_));
+        const size_t esz = is_f64 ? 8 : 4;
+        const size_t chunk_frames = (size_t)plan_tiles(nframes) * kTileFrames;
+        const size_t stage_frames = std::min(nframes, chunk_frames);
+        if (!d_stage_in_.ensure(stage_frames * llrs_len * esz) || !d_stage_out_.ensure(std::max<size_t>(stage_frames * out_len, 1)) ||
+            !d_stage_iters_.ensure(stage_frames))
+            return false;
+        for (size_t f0 = 0; f0 < nframes; f0 += chunk_frames) {
+            size_t nf = std::min(chunk_frames, nframes - f0);
+            LDPC_CUDA_CHECK(cudaMemcpyAsync(d_stage_in_.p, (const uint8_t*)llrs + f0 * llrs_len * esz, nf * llrs_len * esz,
+                                            cudaMemcpyHostToDevice, stream_));
+            if (!run_chunk(d_stage_in_.p, is_f64, llrs_len, nf, max_iterations, d_stage_out_.p, out_len, out_len,
+                           d_stage_iters_.p, stream_))
+                return false;
+            if (out_len)
+                LDPC_CUDA_CHECK(cudaMemcpy2DAsync(out + f0 * out_stride, out_stride, d_stage_out_.p, out_len, out_len, nf,
+                                                  cudaMemcpyDeviceToHost, stream_));
+            LDPC_CUDA_CHECK(cudaMemcpyAsync(iterations + f0, d_stage_iters_.p, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+            LDPC_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        }
+        return true;
+    }
+
+    bool decode_batch_device(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nframes, uint32_t max_iterations,
+                             uint8_t* d_out, size_t out_len, size_t out_stride, int32_t* d_iterations,
+                             cudaStream_t stream) override {
+        if (!check_args(llrs_len, out_len, out_stride)) return false;
+        if (nframes == 0) return true;
+        LDPC_CUDA_CHECK(cudaSetDevice(device_));
+        const size_t esz = is_f64 ? 8 : 4;
+        const size_t chunk_frames = (size_t)plan_tiles(nframes) * kTileFrames;
+        for (size_t f0 = 0; f0 < nframes; f0 += chunk_frames) {
+            size_t nf = std::min(chunk_frames, nframes - f0);
+            if (!run_chunk((const uint8_t*)d_llrs + f0 * llrs_len * esz, is_f64, llrs_len, nf, max_iterations,
+                           d_out + f0 * out_stride, out_len, out_stride, d_iterations + f0, stream))
+                return false;
+        }
+        return true;
+    }
+
+private:
+    bool check_args(size_t llrs_len, size_t out_len, size_t out_stride) {
+        // the reference asserts / panics on these (flooding.rs:56, c_api/decoder.rs:51,:61)
+        if (llrs_len != expected_len_) { set_last_error("llrs_len does not match the code"); return false; }
+        if (out_len > (size_t)g_.n || out_stride < out_len) { set_last_error("output_len larger than the codeword"); return false; }
+        return true;
+    }
+
+    size_t tile_bytes() const {
+        return (size_t)g_.E * kLanes * 4 + (size_t)g_.n * kLanes * 4 + 2 * (size_t)g_.n * kLanes;
+    }
+
+    // tiles per kernel launch: whole waves of resident CTAs, bounded by free HBM
+    int plan_tiles(size_t nframes) {
+        int need = (int)((nframes + kTileFrames - 1) / kTileFrames);
+        int cap = max_tiles_opt_ > 0 ? max_tiles_opt_ : sm_count_ * 4;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            size_t have = ws_tiles_ * tile_bytes();
+            size_t budget = (size_t)((double)(free_b + have) * 0.45);
+            int fit = (int)std::max<size_t>(budget / std::max<size_t>(tile_bytes(), 1), 1);
+            cap = std::min(cap, fit);
+        }
+        return std::max(1, std::min(need, cap));
+    }
+
+    bool ensure_workspace(int tiles) {
+        if ((size_t)tiles <= ws_tiles_) return true;
+        if (!d_msg_.ensure((size_t)tiles * g_.E * kLanes) || !d_inq_.ensure((size_t)tiles * g_.n * kLanes) ||
+            !d_hard_.ensure((size_t)tiles * g_.n * kLanes) || !d_final_.ensure((size_t)tiles * g_.n * kLanes))
+            return false;
+        ws_tiles_ = (size_t)tiles;
+        return true;
+    }
+
+    bool run_chunk(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
+                   size_t out_len, size_t out_stride, int32_t* d_iters, cudaStream_t s) {
+        const int tiles = (int)((nf + kTileFrames - 1) / kTileFrames);
+        if (!ensure_workspace(tiles)) return false;
+        if (!d_iters_tile_.ensure((size_t)tiles * kTileFrames)) return false;
+        cudaEventRecord(ev_[0], s);
+        IngestLaunch in{};
+        in.llrs = d_llrs; in.is_f64 = is_f64; in.llrs_len = llrs_len; in.nframes = nf; in.n = g_.n;
+        in.src_map = punct_ ? d_src_map_.p : nullptr; in.num_tiles = tiles;
+        in.inq_i8 = d_inq_.p; in.hard = d_hard_.p;
+        if (!launch_ingest(in, s)) return false;
+        cudaEventRecord(ev_[1], s);
+        FloodI8Launch fl{};
+        fl.graph = dg_; fl.num_tiles = tiles; fl.msg = d_msg_.p; fl.inq = d_inq_.p; fl.hard = d_hard_.p;
+        fl.final_hard = d_final_.p; fl.iters = d_iters_tile_.p;
+        // a graph the min* rules panic on: run only the pre-check; everything else reports -2
+        fl.max_iter = panics_ ? 0 : (int)std::min<uint32_t>(max_it, 0x7ffffff0u);
+        fl.aminstar = impl_.rule == Rule::Aminstar; fl.jones = impl_.jones; fl.hardlimit = impl_.hardlimit; fl.deg1clip = impl_.deg1clip;
+        if (!launch_flood_i8(fl, s)) return false;
+        cudaEventRecord(ev_[2], s);
+        EmitLaunch em{};
+        em.final_hard = d_final_.p; em.n = g_.n; em.num_tiles = tiles; em.nframes = nf; em.out = d_out; em.out_len = out_len;
+        em.out_stride = out_stride;
+        if (!launch_emit(em, s)) return false;
+        LDPC_CUDA_CHECK(cudaMemcpyAsync(d_iters, d_iters_tile_.p, nf * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        if (panics_ && max_it > 0) {
+            if (!launch_mark_panics(d_iters, nf, s)) return false;
+        }
+        cudaEventRecord(ev_[3], s);
+        stats_.kernel_launches += 3;
+        timed_ = true;
+        return true;
+    }
+
+    bool launch_mark_panics(int32_t* d_iters, size_t nf, cudaStream_t s);
+
+public:
+    // resolves the event timings of the last chunk (synchronises the stream)
+    void resolve_stats() {
+        if (!timed_) return;
+        cudaEventSynchronize(ev_[3]);
+        cudaEventElapsedTime(&stats_.ingest_ms, ev_[0], ev_[1]);
+        cudaEventElapsedTime(&stats_.decode_ms, ev_[1], ev_[2]);
+        cudaEventElapsedTime(&stats_.emit_ms, ev_[2], ev_[3]);
+    }
+
+private:
+    DecoderImplementation impl_;
+    Graph g_;
+    DeviceGraph dg_{};
+    std::unique_ptr<Puncturer> punct_;
+    size_t expected_len_ = 0;
+    bool panics_ = false;
+    int device_ = 0, sm_count_ = 148, max_tiles_opt_ = 0;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool timed_ = false;
+    BatchStats stats_;
+    DevBuf<int> d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_src_map_;
+    DevBuf<uint32_t> d_msg_, d_inq_;
+    DevBuf<uint8_t> d_hard_, d_final_, d_stage_in_, d_stage_out_;
+    DevBuf<int32_t> d_iters_tile_, d_stage_iters_;
+    size_t ws_tiles_ = 0;
+};
+
+__global__ void mark_panics_kernel(int32_t* iters, size_t nf) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nf && iters[i] < 0) iters[i] = -2;
+}
+
+bool GpuDecoder::launch_mark_panics(int32_t* d_iters, size_t nf, cudaStream_t s) {
+    mark_panics_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(d_iters, nf);
+    LDPC_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+}  // namespace
+
+std::unique_ptr<LdpcDecoder> build_decoder(const DecoderImplementation& impl, const Graph& h, const Puncturer* puncturer,
+                                           const DecoderOptions& opt) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_last_error("no CUDA device: this library has no CPU fallback");
+        return nullptr;
+    }
+    auto d = std::make_unique<GpuDecoder>(impl, h);
+    if (!d->init(puncturer, opt)) return nullptr;
+    return d;
+}
+
+void resolve_decoder_stats(LdpcDecoder* d) { static_cast<GpuDecoder*>(d)->resolve_stats(); }
+
+}  // namespace ldpc

@@ -1,0 +1,58 @@
+// ldpc_toolbox_b200/csrc/decoder_impl.hpp — internal launch interfaces between the host-side
+// decoder object (decoder.cu) and the kernels (flood_i8.cu, flood_float.cu, layered.cu, ingest.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "device_common.cuh"
+
+namespace ldpc {
+
+void set_last_error(const std::string& msg);
+const std::string& last_error();
+
+// ---- ingest.cu ---------------------------------------------------------------------------------
+struct IngestLaunch {
+    const void* llrs;        // device, [nframes][llrs_len] f32 or f64 (frame-major, as the caller gave them)
+    bool is_f64;
+    size_t llrs_len;         // per frame (punctured length when a puncturer is attached)
+    size_t nframes;          // frames present; tiles are padded with LLR=+1 (clean all-zero word)
+    int n;                   // codeword length
+    const int* src_map;      // device, n entries: index into the frame's llrs or -1 (punctured -> 0.0); may be null
+    int num_tiles;
+    // outputs (any may be null)
+    uint32_t* inq_i8;        // [tiles][n][32] int8x4: quantised LLRs (arithmetic.rs:690-699)
+    float* in_f32;           // [tiles][n][128] f32 (`llr as f32`)
+    double* in_f64;          // [tiles][n][128] f64
+    uint8_t* hard;           // [tiles][n][32] raw-sign hard decisions (x <= 0.0), 4 bits per lane
+};
+bool launch_ingest(const IngestLaunch& L, cudaStream_t stream);
+
+struct EmitLaunch {
+    const uint8_t* final_hard;   // [tiles][n][32]
+    int n;
+    int num_tiles;
+    size_t nframes;
+    uint8_t* out;                // device, [nframes][out_stride] one 0/1 byte per bit
+    size_t out_len, out_stride;
+};
+bool launch_emit(const EmitLaunch& L, cudaStream_t stream);
+
+// ---- flood_i8.cu -------------------------------------------------------------------------------
+struct FloodI8Launch {
+    DeviceGraph graph;
+    int num_tiles;
+    uint32_t* msg;
+    const uint32_t* inq;
+    uint8_t* hard;
+    uint8_t* final_hard;
+    int32_t* iters;
+    int max_iter;
+    bool aminstar, jones, hardlimit, deg1clip;
+};
+bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream);
+int flood_i8_max_row_degree();
+
+}  // namespace ldpc

@@ -7,13 +7,26 @@ import subprocess
 import numpy as np
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
-SO = os.path.join(ROOT, "oracle", "_build", "libldpc_oracle.so")
+
+
+def _cpu_tag():
+    """The checker is built with -march=native; key the build directory by the host's ISA flags so a
+    library built in the CPU container is never loaded on a GPU box with a different CPU."""
+    import hashlib
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags"))
+    except Exception:
+        flags = "unknown"
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+SO = os.path.join(ROOT, "oracle", "_build", _cpu_tag(), "libldpc_oracle.so")
 
 
 def build(force=False):
     srcs = [os.path.join(ROOT, "oracle", f) for f in ("ldpc_oracle.cpp", "ldpc_oracle_capi.cpp", "ldpc_oracle.hpp")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "OUT=" + SO], stdout=subprocess.DEVNULL)
     return SO
 
 

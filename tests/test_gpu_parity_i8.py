@@ -1,0 +1,144 @@
+"""GPU parity: the CUDA flooding i8 decoders (K1) against the CPU checker, through the C-ABI,
+bit-exact on decoded words AND iteration counts (BASELINE.json north_star).  Needs a B200."""
+import numpy as np
+import pytest
+
+import helpers
+from ldpc_toolbox_b200 import Decoder, codes, implementation_names
+
+pytestmark = pytest.mark.gpu
+
+JOHNSON = "6 4\n2 3\n2 2 2 2 2 2\n3 3 3 3\n1 3\n1 2\n2 4\n1 4\n2 3\n3 4\n1 2 4\n2 3 5\n1 5 6\n3 4 6\n"
+I8_FLOOD = [n for n in implementation_names() if "i8" in n and not n.startswith("HL")]
+
+
+def compare(oracle, alist, impl, llrs, max_iter, puncturing="", out_len=None, label=""):
+    dec = Decoder(alist, impl, puncturing)
+    ref = oracle.decoder(alist, impl, puncturing)
+    out, its = dec.decode_batch(llrs, max_iter, output_len=out_len)
+    rout, rits = ref.decode_batch(llrs, max_iter, out_len=out_len)
+    bad_it = np.nonzero(its != rits)[0]
+    assert bad_it.size == 0, f"{label}{impl}: iteration mismatch at frames {bad_it[:8]}: gpu {its[bad_it[:8]]} ref {rits[bad_it[:8]]}"
+    bad = np.nonzero((out != rout).any(axis=1))[0]
+    assert bad.size == 0, f"{label}{impl}: word mismatch at frames {bad[:8]}"
+    return its
+
+
+def test_a10_vector_and_single_frame_api(oracle):
+    cw = [0, 0, 1, 0, 1, 1]
+    llr = np.array([-1.3863, 1.3863, -1.3863, 1.3863, -1.3863, -1.3863])   # bit 0 flipped
+    for impl, iters in (("Minstarapproxi8", 2), ("Aminstari8", 2)):
+        dec = Decoder(JOHNSON, impl)
+        out, it = dec.decode(llr, 100)
+        assert it == iters and out.tolist() == cw
+        out, it = dec.decode(llr.astype(np.float32), 100, output_len=3)
+        assert it == iters and out.tolist() == cw[:3]
+        out, it = dec.decode(llr, 1)
+        assert it == -1
+        clean = np.array([1.3863 if b == 0 else -1.3863 for b in cw])
+        out, it = dec.decode(clean, 100)
+        assert it == 0 and out.tolist() == cw
+
+
+@pytest.mark.parametrize("impl", I8_FLOOD)
+def test_johnson_all_variants(oracle, impl):
+    rng = np.random.default_rng(11)
+    cws = np.tile(np.array([0, 0, 1, 0, 1, 1], dtype=np.uint8), (300, 1))
+    llrs = np.concatenate([helpers.awgn_llrs(rng, cws[:100], s, np.float64) for s in (0.4, 0.8, 1.3)])
+    llrs[5] = 0.0            # all-erasure frame: zero LLR decides 1
+    llrs[6, 2] = np.nan
+    llrs[7] *= 1e6           # saturates the quantiser
+    compare(oracle, JOHNSON, impl, llrs, 20)
+
+
+@pytest.mark.parametrize("impl", I8_FLOOD)
+def test_random_irregular_codes(oracle, impl):
+    rng = np.random.default_rng(hash(impl) % 2**32)
+    for trial in range(3):
+        n, m = [(96, 48), (200, 80), (64, 40)][trial]
+        alist = helpers.random_code_alist(rng, n, m, col_w=[1, 2, 3, 4, 9], extra_heavy_rows=2 if trial else 0)
+        enc = oracle.encoder(alist) if trial == 99 else None
+        cws = np.zeros((520, n), dtype=np.uint8)   # all-zero word is in every code; i8 rules are still asymmetric in LLR=0
+        llrs = np.concatenate([helpers.awgn_llrs(rng, cws[:130], s) for s in (0.3, 0.6, 0.9, 1.4)])
+        its = compare(oracle, alist, impl, llrs, 12, label=f"trial {trial} ")
+        assert (its == -1).any() or (its > 0).any()
+
+
+def test_ragged_batch_and_strides(oracle):
+    rng = np.random.default_rng(5)
+    alist = helpers.random_code_alist(rng, 120, 60)
+    for nframes in (1, 127, 128, 129, 300):
+        llrs = helpers.awgn_llrs(rng, np.zeros((nframes, 120), dtype=np.uint8), 0.9)
+        compare(oracle, alist, "Minstarapproxi8", llrs, 10, out_len=60, label=f"nframes {nframes} ")
+    dec = Decoder(alist, "Minstarapproxi8")
+    llrs = helpers.awgn_llrs(rng, np.zeros((10, 120), dtype=np.uint8), 0.9)
+    big = np.full((10, 200), 7, dtype=np.uint8)
+    out, its = dec.decode_batch(llrs, 10, output_len=50, out=big[:, :50])
+    assert (big[:, 50:] == 7).all()
+    ref, rits = oracle.decoder(alist, "Minstarapproxi8").decode_batch(llrs, 10, out_len=50)
+    assert (big[:, :50] == ref).all() and (its == rits).all()
+
+
+def test_max_iterations_zero(oracle):
+    rng = np.random.default_rng(6)
+    alist = helpers.random_code_alist(rng, 60, 30)
+    dec = Decoder(alist, "Minstarapproxi8")
+    llrs = helpers.awgn_llrs(rng, np.zeros((40, 60), dtype=np.uint8), 0.7)
+    out, its = dec.decode_batch(llrs, 0)
+    ref = oracle.decoder(alist, "Minstarapproxi8")
+    _, rits = ref.decode_batch(llrs, 0)
+    assert (its == rits).all()                       # 0 for clean frames, -1 otherwise
+    ok = its == 0
+    assert (out[ok] == (llrs[ok] <= 0)).all()
+    # documented deviation: failing frames return the raw-sign hard decision (the reference returns stale state)
+    assert (out[~ok] == (llrs[~ok] <= 0)).all()
+
+
+def test_argument_errors():
+    dec = Decoder(JOHNSON, "Minstarapproxi8")
+    with pytest.raises(ValueError):
+        dec.decode(np.zeros(5), 10)
+    with pytest.raises(ValueError):
+        dec.decode(np.zeros(6), 10, output_len=7)
+    with pytest.raises(ValueError):
+        Decoder(JOHNSON, "minstarapproxi8")
+    with pytest.raises(ValueError):
+        Decoder(JOHNSON, "Minstarapproxi8", "1,x")
+    with pytest.raises(ValueError):
+        Decoder("garbage", "Minstarapproxi8")
+
+
+def test_puncturing_ar4ja(oracle):
+    alist = codes.alist_for("ar4ja:1/2:1024")
+    rng = np.random.default_rng(8)
+    enc = oracle.encoder(alist, "1,1,1,1,0")
+    msgs = rng.integers(0, 2, size=(200, 1024), dtype=np.uint8)
+    tx = np.stack([enc.encode(m, 2048) for m in msgs])
+    sigma = helpers.sigma_for(2.0, 0.5)
+    llrs = helpers.awgn_llrs(rng, tx, sigma)
+    for impl in ("Minstarapproxi8", "Aminstari8Jones", "Minstarapproxi8Deg1Clip"):
+        its = compare(oracle, alist, impl, llrs, 30, puncturing="1,1,1,1,0", out_len=1024)
+    assert (its > 0).any()
+
+
+def test_dvbs2_short(oracle):
+    alist = codes.alist_for("dvbs2:R1_2short")
+    rng = np.random.default_rng(9)
+    enc = oracle.encoder(alist)
+    k = 16200 - 9000
+    msgs, cws = helpers.encoded_frames(enc, rng, k, 16200, 96)
+    for ebn0 in (0.6, 1.4):
+        llrs = helpers.awgn_llrs(rng, cws, helpers.sigma_for(ebn0, k / 16200))
+        compare(oracle, alist, "Minstarapproxi8", llrs, 25, out_len=k, label=f"ebn0 {ebn0} ")
+
+
+def test_dvbs2_normal_r12_north_star(oracle):
+    """BASELINE.json config 3: DVB-S2 n=64800 r=1/2, Minstarapproxi8, 25 iterations."""
+    alist = codes.alist_for("dvbs2:R1_2")
+    rng = np.random.default_rng(10)
+    enc = oracle.encoder(alist)
+    msgs, cws = helpers.encoded_frames(enc, rng, 32400, 64800, 160)
+    llrs = np.concatenate([helpers.awgn_llrs(rng, cws[i * 40:(i + 1) * 40], helpers.sigma_for(e, 0.5))
+                           for i, e in enumerate((0.5, 1.1, 1.25, 2.5))])
+    its = compare(oracle, alist, "Minstarapproxi8", llrs, 25, out_len=32400)
+    assert (its == -1).any() and (its > 0).any()
