@@ -1,0 +1,316 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the hot path (BASELINE.json config 3).
+
+Workload: DVB-S2 normal FECFRAME n=64800 r=1/2, decoder Minstarapproxi8 (flooding), 25 iterations,
+BPSK/AWGN at Eb/N0 = 0.5 dB (below threshold => every frame runs all 25 iterations: fixed work).
+One step = one decode_batch over B frames whose f32 LLRs are already resident in HBM; metric =
+decoded information Gbit/s = k * frames / time (reference src/simulation/ber.rs:574, in Gbit).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm
+  python bench.py --impl reference ...                          CPU arm: the C++ restatement of the
+        reference's CPU path (the Rust crate cannot be built here), all host threads.
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CODE = "dvbs2:R1_2"
+IMPL = "Minstarapproxi8"
+MAX_ITER = 25
+EBN0_DB = 0.5
+N, K_INFO, E = 64800, 32400, 226799
+METRIC = "decoded info Gbit/s (DVB-S2 n=64800 r=1/2 Minstarapproxi8, 25 it)"
+
+
+def algorithmic_bytes(total_iterations: int, frames: int) -> float:
+    """4*E*s_msg bytes per frame-iteration + f32 LLR in + packed bits out."""
+    return total_iterations * 4.0 * E * 1 + frames * (N * 4 + N / 8)
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------
+def synth_llrs_device(torch, dev, frames: int, seed: int, chunk: int = 4096):
+    """Random messages -> product's own systematic encoder (C-ABI) -> BPSK -> AWGN (torch.randn on
+    the device) -> f32 LLRs [frames][n] resident in HBM.  64 distinct codewords are cycled."""
+    from ldpc_toolbox_b200 import Encoder, codes
+    alist = codes.cached_alist_path(CODE)
+    enc = Encoder(alist)
+    rng = np.random.default_rng(seed)
+    ncw = 64
+    cws = np.stack([enc.encode(rng.integers(0, 2, K_INFO, dtype=np.uint8), N) for _ in range(ncw)])
+    sym = torch.from_numpy(np.where(cws == 1, 1.0, -1.0).astype(np.float32)).to(dev)      # bit0 -> -1, bit1 -> +1
+    rate = K_INFO / N
+    sigma = float(np.sqrt(0.5 / (rate * 10 ** (np.float32(EBN0_DB) / 10))))
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    llrs = torch.empty((frames, N), dtype=torch.float32, device=dev)
+    for f0 in range(0, frames, chunk):
+        nf = min(chunk, frames - f0)
+        idx = (torch.arange(f0, f0 + nf, device=dev) % ncw)
+        y = sym[idx] + sigma * torch.randn((nf, N), generator=g, device=dev, dtype=torch.float32)
+        llrs[f0:f0 + nf] = (-2.0 / sigma**2) * y
+    return llrs, alist, cws
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this framework has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from ldpc_toolbox_b200 import Decoder
+
+    sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    tiles = args.tiles if args.tiles > 0 else sm * 4
+    frames = tiles * 128
+    llrs, alist, cws = synth_llrs_device(torch, dev, frames, seed=0x5EED + rank)
+    dec = Decoder(alist, IMPL, device=local, max_tiles=tiles)
+    out = torch.empty((frames, K_INFO), dtype=torch.uint8, device=dev)
+    iters = torch.empty((frames,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        dec.decode_batch_ptr(llrs.data_ptr(), False, N, frames, MAX_ITER, out.data_ptr(), K_INFO, K_INFO, iters.data_ptr(),
+                             device=True, stream=stream.cuda_stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record(stream)
+        bp = []
+        for _ in range(args.steps):
+            step()
+            bp.append(dec.last_timing()["decode_ms"])     # library events around the BP kernel, same stream
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    # correctness of the timed work: info bits of the decoded frames vs what was sent
+    it_host = iters.cpu().numpy()
+    total_iters = int(np.where(it_host < 0, MAX_ITER, it_host).sum())
+    # dominant kernel: device time of the BP kernel alone (events recorded inside the library on
+    # the launching stream around the flood kernel of the last step)
+    tm = dec.last_timing()
+    bp_ms = float(np.mean(bp))
+    peak, peak_src = measured_hbm_peak()
+    alg = algorithmic_bytes(total_iters, frames)
+    achieved = alg / (bp_ms * 1e-3) / 1e9
+
+    # ---- e2e: same metric through the public host-buffer call, H2D + D2H inside the timed region
+    e2e_frames = min(frames, args.e2e_tiles * 128)
+    h_llrs = torch.empty((e2e_frames, N), dtype=torch.float32).pin_memory()
+    h_llrs.copy_(llrs[:e2e_frames].cpu())
+    h_out = torch.empty((e2e_frames, K_INFO), dtype=torch.uint8).pin_memory()
+    h_it = torch.empty((e2e_frames,), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        dec.decode_batch_ptr(h_llrs.data_ptr(), False, N, e2e_frames, MAX_ITER, h_out.data_ptr(), K_INFO, K_INFO, h_it.data_ptr(),
+                             device=False)
+
+    e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    sent = torch.from_numpy(cws[:, :K_INFO])
+    idx = torch.arange(e2e_frames) % cws.shape[0]
+    bit_errors = int((h_out != sent[idx]).sum())
+    e2e_gbps = K_INFO * e2e_frames * e2e_steps * world / e2e_s / 1e9
+
+    value = K_INFO * frames * args.steps * world / (ms_total * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": round(value, 4), "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "i8", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[2]: DVB-S2 normal n=64800 r=1/2, Minstarapproxi8 flooding, max_iter 25, "
+                               f"BPSK/AWGN Eb/N0 {EBN0_DB} dB (fixed work: avg iterations {total_iters / frames:.2f})",
+                   "frames_per_gpu_per_step": frames, "tiles_per_gpu": tiles,
+                   "l2": "inputs (%.1f GB LLRs + %.1f GB message state per step) exceed the 126 MB L2" % (frames * N * 4 / 1e9, frames * E / 1e9),
+                   "edge_msgs_per_s": round(2.0 * E * total_iters * world / (ms_total / args.steps * 1e-3), 1)},
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": None, "kernel": "flood_i8_kernel", "kernel_ms": round(bp_ms, 3), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg},
+        "e2e": {"value": round(e2e_gbps, 4), "unit": "Gbit/s", "h2d_bytes_per_step": e2e_frames * N * 4,
+                "d2h_bytes_per_step": e2e_frames * (K_INFO + 4), "frames_per_step": e2e_frames, "info_bit_errors": bit_errors},
+        "gpu_launches": 3 * args.steps,
+        "stage_ms_last_step": {k: round(v, 3) for k, v in tm.items() if k.endswith("_ms")},
+        "clocks": clocks.summary(),
+    }
+    if rank == 0:
+        if args.cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(sample_seconds=args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
+def _cpu_sample(nframes: int, seed: int):
+    """Same workload on the host: LLR frames for the oracle (numpy)."""
+    from ldpc_toolbox_b200 import Encoder, codes
+    alist_path = codes.cached_alist_path(CODE)
+    enc = Encoder(alist_path)
+    rng = np.random.default_rng(seed)
+    cws = np.stack([enc.encode(rng.integers(0, 2, K_INFO, dtype=np.uint8), N) for _ in range(min(nframes, 16))])
+    sigma = float(np.sqrt(0.5 / ((K_INFO / N) * 10 ** (np.float32(EBN0_DB) / 10))))
+    sym = np.where(cws == 1, 1.0, -1.0).astype(np.float32)[np.arange(nframes) % cws.shape[0]]
+    y = sym + sigma * rng.standard_normal(sym.shape, dtype=np.float32)
+    return open(alist_path).read(), (-2.0 / sigma**2 * y).astype(np.float32)
+
+
+def cpu_baseline(sample_seconds: float = 15.0, linear_search: bool = False):
+    """The CPU restatement of the reference's path (oracle/, "port") on all host cores, on a
+    bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oraclelib
+    o = oraclelib.load()
+    cores = os.cpu_count() or 1
+    alist, llrs = _cpu_sample(cores * 2, seed=77)
+    dec = o.decoder(alist, IMPL)
+    dec.set_linear_search(linear_search)
+    t0 = time.perf_counter()
+    dec.decode_batch(llrs, MAX_ITER, out_len=K_INFO, nthreads=cores)
+    probe = time.perf_counter() - t0
+    nframes = int(max(cores * 2, min(4096, cores * 2 * sample_seconds / max(probe, 1e-3))))
+    nframes -= nframes % cores
+    alist, llrs = _cpu_sample(nframes, seed=78)
+    t0 = time.perf_counter()
+    _, its = dec.decode_batch(llrs, MAX_ITER, out_len=K_INFO, nthreads=cores)
+    el = time.perf_counter() - t0
+    return {"value": round(K_INFO * nframes / el / 1e9, 6), "unit": "Gbit/s", "cores": cores, "kind": "port",
+            "sample": f"{nframes} frames of the same workload in {el:.1f} s, C++ restatement of the reference CPU path "
+                      f"(Rust toolchain unavailable), {'linear-search send' if linear_search else 'direct edge indexing'}, "
+                      f"avg iterations {float(np.where(its < 0, MAX_ITER, its).mean()):.2f}",
+            "frames_per_s": round(nframes / el, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    vals, samples = [], []
+    for _ in range(args.warmup + args.steps):
+        b = cpu_baseline(sample_seconds=min(args.cpu_seconds, 10.0), linear_search=args.faithful_send)
+        vals.append(b)
+    timed = vals[args.warmup:] or vals
+    v = float(np.mean([b["value"] for b in timed]))
+    fps = float(np.mean([b["frames_per_s"] for b in timed]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 6), "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 * K_INFO * 1 / max(v * 1e9, 1e-9), 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "i8", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[2]: DVB-S2 normal n=64800 r=1/2, Minstarapproxi8 flooding, max_iter 25, "
+                               f"BPSK/AWGN Eb/N0 {EBN0_DB} dB", "frames_per_s": fps},
+        "cpu_baseline": dict(timed[-1], value=round(v, 6)),
+        "e2e": {"value": round(v, 6), "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tiles", type=int, default=0, help="128-frame tiles per GPU per step (default 4 per SM)")
+    ap.add_argument("--e2e-tiles", type=int, default=148)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--faithful-send", action="store_true", help="reference arm: time the linear-search send of decoder.rs:111-117")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
