@@ -130,7 +130,7 @@ def run_ours(args):
     from ldpc_toolbox_b200 import Decoder
 
     sm = torch.cuda.get_device_properties(dev).multi_processor_count
-    tiles = args.tiles if args.tiles > 0 else sm * 4
+    tiles = args.tiles if args.tiles > 0 else sm * 8      # 2 CTAs of 512 frames per SM
     frames = tiles * 128
     llrs, alist, cws = synth_llrs_device(torch, dev, frames, seed=0x5EED + rank)
     dec = Decoder(alist, IMPL, device=local, max_tiles=tiles)
@@ -300,7 +300,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--tiles", type=int, default=0, help="128-frame tiles per GPU per step (default 4 per SM)")
+    ap.add_argument("--tiles", type=int, default=0, help="frames per GPU per step / 128 (default 8 per SM = two 512-frame tiles per SM)")
     ap.add_argument("--e2e-tiles", type=int, default=148)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")

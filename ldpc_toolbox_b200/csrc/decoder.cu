@@ -6,6 +6,7 @@
 #include "decoder.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "decoder_impl.hpp"
@@ -93,9 +94,12 @@ public:
             return false;
         dg_.n = g_.n; dg_.m = g_.m; dg_.E = g_.E;
         dg_.row_ptr = d_row_ptr_.p; dg_.col_idx = d_col_idx_.p; dg_.col_ptr = d_col_ptr_.p; dg_.col_edge = d_col_edge_.p;
+        if (!build_var_classes()) return false;
         LDPC_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
         for (auto& e : ev_) LDPC_CUDA_CHECK(cudaEventCreate(&e));
         max_tiles_opt_ = opt.max_tiles;
+        nw_opt_ = opt.words_per_lane;
+        if (const char* e = getenv("LDPC_B200_NW")) nw_opt_ = atoi(e);
         return true;
     }
 
@@ -122,7 +126,7 @@ public:
         if (nframes == 0) return true;
         LDPC_CUDA_CHECK(cudaSetDevice(device_));
         const size_t esz = is_f64 ? 8 : 4;
-        const size_t chunk_frames = (size_t)plan_tiles(nframes) * kTileFrames;
+        const size_t chunk_frames = plan_chunk_frames(nframes);
         const size_t stage_frames = std::min(nframes, chunk_frames);
         if (!d_stage_in_.ensure(stage_frames * llrs_len * esz) || !d_stage_out_.ensure(std::max<size_t>(stage_frames * out_len, 1)) ||
             !d_stage_iters_.ensure(stage_frames))
@@ -150,7 +154,7 @@ public:
         if (nframes == 0) return true;
         LDPC_CUDA_CHECK(cudaSetDevice(device_));
         const size_t esz = is_f64 ? 8 : 4;
-        const size_t chunk_frames = (size_t)plan_tiles(nframes) * kTileFrames;
+        const size_t chunk_frames = plan_chunk_frames(nframes);
         for (size_t f0 = 0; f0 < nframes; f0 += chunk_frames) {
             size_t nf = std::min(chunk_frames, nframes - f0);
             if (!run_chunk((const uint8_t*)d_llrs + f0 * llrs_len * esz, is_f64, llrs_len, nf, max_iterations,
@@ -168,47 +172,88 @@ private:
         return true;
     }
 
-    size_t tile_bytes() const {
-        return (size_t)g_.E * kLanes * 4 + (size_t)g_.n * kLanes * 4 + 2 * (size_t)g_.n * kLanes;
+    // words per lane for a batch: 512-frame tiles (512-byte HBM granules) once they can fill the GPU
+    int pick_nw(size_t nframes) const {
+        if (nw_opt_ == 1 || nw_opt_ == 4) return nw_opt_;
+        return nframes >= (size_t)sm_count_ * 512 ? 4 : 1;
     }
 
-    // tiles per kernel launch: whole waves of resident CTAs, bounded by free HBM
-    int plan_tiles(size_t nframes) {
-        int need = (int)((nframes + kTileFrames - 1) / kTileFrames);
-        int cap = max_tiles_opt_ > 0 ? max_tiles_opt_ : sm_count_ * 4;
+    // HBM bytes of decoder state per 128 frames
+    size_t bytes_per_128() const {
+        return (size_t)g_.E * kLanes * 5 + (size_t)g_.n * kLanes * 4 + 2 * (size_t)g_.n * kLanes;
+    }
+
+    // frames per kernel launch: whole waves of resident CTAs, bounded by free HBM
+    size_t plan_chunk_frames(size_t nframes) {
+        const int nw = pick_nw(nframes);
+        const size_t tf = (size_t)kTileFrames * nw;
+        size_t need = (nframes + tf - 1) / tf;
+        size_t cap = max_tiles_opt_ > 0 ? std::max<size_t>((size_t)max_tiles_opt_ / nw, 1) : (size_t)sm_count_ * (nw == 4 ? 2 : 4);
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            size_t have = ws_tiles_ * tile_bytes();
-            size_t budget = (size_t)((double)(free_b + have) * 0.45);
-            int fit = (int)std::max<size_t>(budget / std::max<size_t>(tile_bytes(), 1), 1);
+            size_t budget = (size_t)((double)(free_b + ws_bytes_) * 0.45);
+            size_t fit = std::max<size_t>(budget / std::max<size_t>(bytes_per_128() * nw, 1), 1);
             cap = std::min(cap, fit);
         }
-        return std::max(1, std::min(need, cap));
+        return std::max<size_t>(1, std::min(need, cap)) * tf;
     }
 
-    bool ensure_workspace(int tiles) {
-        if ((size_t)tiles <= ws_tiles_) return true;
-        if (!d_msg_.ensure((size_t)tiles * g_.E * kLanes) || !d_inq_.ensure((size_t)tiles * g_.n * kLanes) ||
-            !d_hard_.ensure((size_t)tiles * g_.n * kLanes) || !d_final_.ensure((size_t)tiles * g_.n * kLanes))
+    // variables bucketed by degree so the variable pass runs fixed-degree, unrolled code
+    bool build_var_classes() {
+        std::vector<int> var_list, var_edges;
+        vc_ = VarClasses{};
+        int k = 0;
+        auto deg_of = [&](int v) { return g_.col_ptr[(size_t)v + 1] - g_.col_ptr[(size_t)v]; };
+        for (int d = 1; d <= 8; ++d) {
+            int before = (int)var_list.size();
+            int ebefore = (int)var_edges.size();
+            for (int v = 0; v < g_.n; ++v) {
+                if (deg_of(v) != d) continue;
+                var_list.push_back(v);
+                for (int q = g_.col_ptr[(size_t)v]; q < g_.col_ptr[(size_t)v + 1]; ++q) var_edges.push_back(g_.col_edge[(size_t)q]);
+            }
+            if ((int)var_list.size() == before) continue;
+            vc_.deg[k] = d; vc_.off[k] = before; vc_.edge_off[k] = ebefore;
+            ++k;
+        }
+        int before = (int)var_list.size();
+        for (int v = 0; v < g_.n; ++v)
+            if (deg_of(v) > 8) var_list.push_back(v);
+        if ((int)var_list.size() != before) { vc_.deg[k] = 0; vc_.off[k] = before; vc_.edge_off[k] = 0; ++k; }
+        vc_.off[k] = (int)var_list.size();
+        vc_.num_classes = k;
+        if (!d_var_list_.upload(var_list) || !d_var_edges_.upload(var_edges)) return false;
+        vc_.var_list = d_var_list_.p;
+        vc_.var_edges = d_var_edges_.p;
+        return true;
+    }
+
+    bool ensure_workspace(size_t tiles, int nw) {
+        const size_t hb = nw == 4 ? 2 : 1;
+        if (!d_msg_.ensure(tiles * g_.E * kLanes * nw) || !d_hbit_.ensure(std::max<size_t>(tiles * g_.E * kLanes * hb, 1)) ||
+            !d_inq_.ensure(tiles * g_.n * kLanes * nw) || !d_hard_.ensure(tiles * g_.n * kLanes * hb) ||
+            !d_final_.ensure(tiles * g_.n * kLanes * hb))
             return false;
-        ws_tiles_ = (size_t)tiles;
+        ws_bytes_ = (d_msg_.count + d_inq_.count) * 4 + d_hbit_.count + d_hard_.count + d_final_.count;
         return true;
     }
 
     bool run_chunk(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
                    size_t out_len, size_t out_stride, int32_t* d_iters, cudaStream_t s) {
-        const int tiles = (int)((nf + kTileFrames - 1) / kTileFrames);
-        if (!ensure_workspace(tiles)) return false;
-        if (!d_iters_tile_.ensure((size_t)tiles * kTileFrames)) return false;
+        const int nw = pick_nw(nf);
+        const size_t tf = (size_t)kTileFrames * nw;
+        const int tiles = (int)((nf + tf - 1) / tf);
+        if (!ensure_workspace((size_t)tiles, nw)) return false;
+        if (!d_iters_tile_.ensure((size_t)tiles * tf)) return false;
         cudaEventRecord(ev_[0], s);
         IngestLaunch in{};
         in.llrs = d_llrs; in.is_f64 = is_f64; in.llrs_len = llrs_len; in.nframes = nf; in.n = g_.n;
-        in.src_map = punct_ ? d_src_map_.p : nullptr; in.num_tiles = tiles;
+        in.src_map = punct_ ? d_src_map_.p : nullptr; in.num_tiles = tiles; in.words_per_lane = nw;
         in.inq_i8 = d_inq_.p; in.hard = d_hard_.p;
         if (!launch_ingest(in, s)) return false;
         cudaEventRecord(ev_[1], s);
         FloodI8Launch fl{};
-        fl.graph = dg_; fl.num_tiles = tiles; fl.msg = d_msg_.p; fl.inq = d_inq_.p; fl.hard = d_hard_.p;
+        fl.graph = dg_; fl.classes = vc_; fl.num_tiles = tiles; fl.words_per_lane = nw; fl.msg = d_msg_.p; fl.hbit = d_hbit_.p; fl.inq = d_inq_.p; fl.raw0 = d_hard_.p;
         fl.final_hard = d_final_.p; fl.iters = d_iters_tile_.p;
         // a graph the min* rules panic on: run only the pre-check; everything else reports -2
         fl.max_iter = panics_ ? 0 : (int)std::min<uint32_t>(max_it, 0x7ffffff0u);
@@ -216,7 +261,7 @@ private:
         if (!launch_flood_i8(fl, s)) return false;
         cudaEventRecord(ev_[2], s);
         EmitLaunch em{};
-        em.final_hard = d_final_.p; em.n = g_.n; em.num_tiles = tiles; em.nframes = nf; em.out = d_out; em.out_len = out_len;
+        em.final_hard = d_final_.p; em.n = g_.n; em.num_tiles = tiles; em.words_per_lane = nw; em.nframes = nf; em.out = d_out; em.out_len = out_len;
         em.out_stride = out_stride;
         if (!launch_emit(em, s)) return false;
         LDPC_CUDA_CHECK(cudaMemcpyAsync(d_iters, d_iters_tile_.p, nf * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
@@ -248,16 +293,17 @@ private:
     std::unique_ptr<Puncturer> punct_;
     size_t expected_len_ = 0;
     bool panics_ = false;
-    int device_ = 0, sm_count_ = 148, max_tiles_opt_ = 0;
+    int device_ = 0, sm_count_ = 148, max_tiles_opt_ = 0, nw_opt_ = 0;
+    size_t ws_bytes_ = 0;
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timed_ = false;
     BatchStats stats_;
-    DevBuf<int> d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_src_map_;
+    DevBuf<int> d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_src_map_, d_var_list_, d_var_edges_;
+    VarClasses vc_{};
     DevBuf<uint32_t> d_msg_, d_inq_;
-    DevBuf<uint8_t> d_hard_, d_final_, d_stage_in_, d_stage_out_;
+    DevBuf<uint8_t> d_hbit_, d_hard_, d_final_, d_stage_in_, d_stage_out_;
     DevBuf<int32_t> d_iters_tile_, d_stage_iters_;
-    size_t ws_tiles_ = 0;
 };
 
 __global__ void mark_panics_kernel(int32_t* iters, size_t nf) {

@@ -54,7 +54,8 @@ public:
 
 struct DecoderOptions {
     int device = -1;                 // -1: current device
-    int max_tiles = 0;               // 0: automatic (a multiple of the SM count that fits in free HBM)
+    int max_tiles = 0;               // frames per launch / 128; 0: automatic (whole waves of CTAs that fit in free HBM)
+    int words_per_lane = 0;          // int8 decoders: 1 = 128-frame tiles, 4 = 512-frame tiles, 0 = by batch size
 };
 
 // DecoderFactory::build_decoder.  Returns nullptr and sets last_error() on failure.

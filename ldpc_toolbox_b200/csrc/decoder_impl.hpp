@@ -22,32 +22,51 @@ struct IngestLaunch {
     int n;                   // codeword length
     const int* src_map;      // device, n entries: index into the frame's llrs or -1 (punctured -> 0.0); may be null
     int num_tiles;
+    int words_per_lane;      // 1: 128-frame tiles, 4: 512-frame tiles (int8 decoders only)
     // outputs (any may be null)
-    uint32_t* inq_i8;        // [tiles][n][32] int8x4: quantised LLRs (arithmetic.rs:690-699)
+    uint32_t* inq_i8;        // [tiles][n][32][NW] int8x4: quantised LLRs (arithmetic.rs:690-699)
     float* in_f32;           // [tiles][n][128] f32 (`llr as f32`)
     double* in_f64;          // [tiles][n][128] f64
-    uint8_t* hard;           // [tiles][n][32] raw-sign hard decisions (x <= 0.0), 4 bits per lane
+    void* hard;              // [tiles][n][32] raw-sign hard decisions (x <= 0.0), 4*NW bits per lane (u8 / u16)
 };
 bool launch_ingest(const IngestLaunch& L, cudaStream_t stream);
 
 struct EmitLaunch {
-    const uint8_t* final_hard;   // [tiles][n][32]
+    const void* final_hard;      // [tiles][n][32] u8 (NW=1) or u16 (NW=4)
     int n;
     int num_tiles;
+    int words_per_lane;
     size_t nframes;
     uint8_t* out;                // device, [nframes][out_stride] one 0/1 byte per bit
     size_t out_len, out_stride;
 };
 bool launch_emit(const EmitLaunch& L, cudaStream_t stream);
 
+// Variables grouped by degree (host-built, device-resident): class k holds the variables
+// var_list[off[k] .. off[k+1]) which all have degree deg[k] (1..8), with their row-major edge ids
+// flattened in cols[v] order at var_edges[edge_off[k] + i*deg[k] + j].  One trailing class with
+// deg[k] = 0 collects every variable of degree > 8 (edges looked up through col_ptr / col_edge).
+// Degree-0 variables are in no class.
+struct VarClasses {
+    int num_classes;
+    int deg[10];
+    int off[11];
+    int edge_off[10];
+    const int* var_list;
+    const int* var_edges;
+};
+
 // ---- flood_i8.cu -------------------------------------------------------------------------------
 struct FloodI8Launch {
     DeviceGraph graph;
+    VarClasses classes;
     int num_tiles;
+    int words_per_lane;      // 1 or 4
     uint32_t* msg;
+    void* hbit;
     const uint32_t* inq;
-    uint8_t* hard;
-    uint8_t* final_hard;
+    const void* raw0;
+    void* final_hard;
     int32_t* iters;
     int max_iter;
     bool aminstar, jones, hardlimit, deg1clip;

@@ -1,25 +1,31 @@
 // ldpc_toolbox_b200/csrc/flood_i8.cu — K1: flooding-schedule BP with the reference's 8-bit
 // arithmetics (16 variants), bit-exact.
 //
-// Replaces, for a whole tile of 128 frames at a time:
-//   flooding::Decoder::decode            reference src/decoder/flooding.rs:51-125
+// Replaces, for a whole tile of frames at a time:
+//   flooding::Decoder::decode             reference src/decoder/flooding.rs:51-125
 //   Minstarapproxi8*::send_check_messages reference src/decoder/arithmetic.rs:718-754
 //   Aminstari8*::send_check_messages      reference src/decoder/arithmetic.rs:1130-1192
 //   impl_send_var_messages_i8             reference src/decoder/arithmetic.rs:622-654
 //   check_llrs / hard_decisions           reference src/decoder.rs:157-174
 //
 // One CTA owns one tile for the whole decode (all iterations); its warps split the check nodes
-// (check pass) and the variable nodes (variable pass).  Messages live in ONE array msg[E][32]
-// (uint32 = 4 frames) in row-major edge order: the check pass reads v->c values and overwrites
-// them in place with c->v values, the variable pass does the reverse.  Every access is a
-// 128-byte line.  The syndrome of iteration i is evaluated during the check pass of iteration
-// i+1 from a compact hard-decision plane (4 bits per lane), so early termination costs no extra
-// pass over the messages; iteration 0 is the reference's pre-check on the raw LLR signs.
+// (check pass) and the variable nodes (variable pass).  A tile is 32 lanes x NW words x 4 frames
+// (NW = 1: 128 frames, 128-byte lines; NW = 4: 512 frames, 512-byte lines moved with 128-bit
+// loads — random 512-byte granules stream HBM at ~6-7 TB/s where 128-byte ones stop near
+// 3.6-4 TB/s, tools/membench.cu).  Messages live in ONE array msg[E][32][NW] (uint32 = 4 frames)
+// in row-major edge order: the check pass reads v->c values and overwrites them in place with
+// c->v values, the variable pass does the reverse.  Hard decisions are kept per EDGE
+// (hbit[E][32], 4*NW bits per lane) so a check reads the bits of its variables from the same
+// contiguous span as its messages: the syndrome of iteration i is evaluated during the check pass
+// of iteration i+1 with no gather and no extra pass; iteration 0 is the reference's pre-check on
+// the raw LLR signs.
 //
 // Exactness notes: the min* fold g(a,b)=max(0,min(a,b)-T[|a-b|]) is not
 // associative, so for every excluded edge j the others are folded left-to-right in row order;
-// the only sharing is the common prefix fold(x_0..x_{j-1}).  T is a 128-entry table in shared
-// memory (exactly one 4-byte word per bank => conflict-free for any index pattern).
+// the only sharing is the common prefix fold(x_0..x_{j-1}).  With d = a - acc,
+//      g(a, acc) = max(0, acc + U[d]),   U[d] = min(d, 0) - T[|d|]
+// so one fold step is: subtract, one table read, one fused add-max(0) (VIADDMNMX.RELU).
+// U is a 255-entry int8 table in shared memory.
 #include <string>
 
 #include "decoder_impl.hpp"
@@ -31,32 +37,62 @@ namespace {
 
 struct FloodI8Params {
     DeviceGraph g;
-    uint32_t* msg;          // [tiles][E][32]
-    const uint32_t* inq;    // [tiles][n][32]   quantised channel LLRs (int8 x4)
-    uint8_t* hard;          // [tiles][n][32]   4 hard bits per lane; iteration 0 = raw LLR signs
-    uint8_t* final_hard;    // [tiles][n][32]   snapshot taken when a frame stops
-    int32_t* iters;         // [tiles*128]      iterations, or -1 on failure
+    VarClasses vc;
+    uint32_t* msg;          // [tiles][E][32][NW]
+    void* hbit;             // [tiles][E][32]     hard decision of the edge's variable, 4*NW bits per lane
+    const uint32_t* inq;    // [tiles][n][32][NW] quantised channel LLRs (int8 x4 per word)
+    const void* raw0;       // [tiles][n][32]     raw-sign hard decisions (x <= 0.0), 4*NW bits per lane
+    void* final_hard;       // [tiles][n][32]     snapshot taken when a frame stops
+    int32_t* iters;         // [tiles*128*NW]     iterations, or -1 on failure
     int max_iter;
     int jones, deg1clip;
 };
 
 constexpr int kWarps = 8;            // warps per CTA
-constexpr int kMaxUnrollD = 10;      // check degrees with a fully unrolled register path
 constexpr int kMaxGenericD = 64;     // larger rows are rejected when the decoder is built
 
-// g(a, acc) of arithmetic.rs:741 on non-negative ints; negT[t] = -T[t]
-__device__ __forceinline__ int gop(int a, int acc, const int8_t* __restrict__ negT) {
-    int mn = min(a, acc);
-    int t = a + acc - 2 * mn;                       // |a - acc|
-    return __viaddmax_s32_relu(mn, (int)negT[t], 0);  // max(mn - T[t], 0)
+template <int NW> struct Lane { uint32_t w[NW]; };
+template <int NW> struct HBitsT { using type = uint8_t; };
+template <> struct HBitsT<4> { using type = uint16_t; };
+
+template <int NW>
+__device__ __forceinline__ Lane<NW> ld_lane(const uint32_t* base, size_t node, int lane) {
+    Lane<NW> r;
+    const uint32_t* p = base + (node * kLanes + lane) * NW;
+    if (NW == 4) {
+        uint4 v = __ldcg(reinterpret_cast<const uint4*>(p));
+        r.w[0] = v.x; r.w[1 % NW] = v.y; r.w[2 % NW] = v.z; r.w[3 % NW] = v.w;
+    } else {
+        r.w[0] = __ldcg(p);
+    }
+    return r;
+}
+template <int NW>
+__device__ __forceinline__ void st_lane(uint32_t* base, size_t node, int lane, const Lane<NW>& v) {
+    uint32_t* p = base + (node * kLanes + lane) * NW;
+    if (NW == 4) __stcg(reinterpret_cast<uint4*>(p), make_uint4(v.w[0], v.w[1 % NW], v.w[2 % NW], v.w[3 % NW]));
+    else __stcg(p, v.w[0]);
+}
+
+struct Tables {
+    int8_t U[256];      // U[d + 127], d = a - acc in [-127, 127]
+    int8_t Tp[128];     // T[t]
+};
+
+__device__ __forceinline__ int table_T(int t) {
+    // T[t] = round(8 ln(1 + e^{-t/8})) = #{theta in {1,3,5,9,13,22} : t < theta}  
+    return (t < 1) + (t < 3) + (t < 5) + (t < 9) + (t < 13) + (t < 22);
+}
+
+// g(a, acc) of arithmetic.rs:741 on non-negative ints
+__device__ __forceinline__ int gop(int a, int acc, const Tables& tb) {
+    return __viaddmax_s32_relu(acc, (int)tb.U[a - acc + 127], 0);
 }
 
 // h(a, acc) of arithmetic.rs:1155-1157
-__device__ __forceinline__ int hop(int a, int acc, const int8_t* __restrict__ negT) {
-    int mn = min(a, acc);
-    int t = a + acc - 2 * mn;
+__device__ __forceinline__ int hop(int a, int acc, const Tables& tb) {
     int s = min(a + acc, 127);                      // i8 saturating_add
-    return max(mn + (int)negT[t] - (int)negT[s], 0);
+    return max(acc + (int)tb.U[a - acc + 127] + (int)tb.Tp[s], 0);
 }
 
 __device__ __forceinline__ int hardlimit(int mag) { return mag >= 100 ? 127 : mag; }   // arithmetic.rs:812-824
@@ -69,11 +105,12 @@ __device__ __forceinline__ uint32_t apply_signs(uint32_t mag, uint32_t sgn) {
     return ((mag ^ m7) + m1) ^ sgn;
 }
 
-template <int D, bool HLIM>
-__device__ __forceinline__ void check_minstar(uint32_t* __restrict__ mrow, const int8_t* __restrict__ negT) {
-    uint32_t x[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) x[j] = ld_stream(mrow + j * kLanes);
+__device__ __forceinline__ int mag_of(uint32_t x, int f) { return abs((int)(int8_t)(x >> (8 * f))); }
+
+// One word (4 frames) of a degree-D check: x[0..D) in, c->v words out (in place).
+// Frame slots whose bit is set in `skip` (every lane's frame there has stopped) are not computed.
+template <int D, bool AMIN, bool HLIM>
+__device__ __forceinline__ void check_word(uint32_t (&x)[D], uint32_t skip, const Tables& tb) {
     uint32_t S = 0;
 #pragma unroll
     for (int j = 0; j < D; ++j) S ^= x[j];
@@ -82,25 +119,38 @@ __device__ __forceinline__ void check_minstar(uint32_t* __restrict__ mrow, const
     for (int j = 0; j < D; ++j) om[j] = 0;
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
+        if (skip >> f & 1) continue;
         int a[D], r[D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) a[j] = abs((int)(int8_t)(x[j] >> (8 * f)));
-        if (D == 2) {
+        for (int j = 0; j < D; ++j) a[j] = mag_of(x[j], f);
+        if (AMIN) {
+            int amin = a[0], arg = 0;                // first minimum (min_by_key)
+#pragma unroll
+            for (int j = 1; j < D; ++j)
+                if (a[j] < amin) { amin = a[j]; arg = j; }
+            int delta = -1;
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                if (j != arg) delta = delta < 0 ? a[j] : hop(a[j], delta, tb);
+            int d2 = hop(delta, amin, tb);
+#pragma unroll
+            for (int j = 0; j < D; ++j) r[j] = j == arg ? delta : d2;
+        } else if (D == 2) {
             r[0] = a[1];
             r[1] = a[0];
         } else {
             int acc = a[1];
 #pragma unroll
-            for (int i = 2; i < D; ++i) acc = gop(a[i], acc, negT);
+            for (int i = 2; i < D; ++i) acc = gop(a[i], acc, tb);
             r[0] = acc;
             int P = a[0];                            // fold(x_0 .. x_{j-1})
 #pragma unroll
             for (int j = 1; j < D; ++j) {
                 acc = P;
 #pragma unroll
-                for (int i = j + 1; i < D; ++i) acc = gop(a[i], acc, negT);
+                for (int i = j + 1; i < D; ++i) acc = gop(a[i], acc, tb);
                 r[j] = acc;
-                if (j < D - 1) P = gop(a[j], P, negT);
+                if (j < D - 1) P = gop(a[j], P, tb);
             }
         }
 #pragma unroll
@@ -110,109 +160,72 @@ __device__ __forceinline__ void check_minstar(uint32_t* __restrict__ mrow, const
         }
     }
 #pragma unroll
-    for (int j = 0; j < D; ++j) st_stream(mrow + j * kLanes, apply_signs(om[j], (S ^ x[j]) & 0x80808080u));
+    for (int j = 0; j < D; ++j) x[j] = apply_signs(om[j], (S ^ x[j]) & 0x80808080u);
 }
 
-template <int D, bool HLIM>
-__device__ __forceinline__ void check_aminstar(uint32_t* __restrict__ mrow, const int8_t* __restrict__ negT) {
-    uint32_t x[D];
+template <int NW, int MAXD, int D, bool AMIN, bool HLIM>
+__device__ __forceinline__ void check_fixed(Lane<NW> (&x)[MAXD], uint32_t* __restrict__ msg, size_t e0, int lane,
+                                            uint32_t skip, const Tables& tb) {
 #pragma unroll
-    for (int j = 0; j < D; ++j) x[j] = ld_stream(mrow + j * kLanes);
-    uint32_t S = 0;
+    for (int q = 0; q < NW; ++q) {
+        if (((skip >> (4 * q)) & 0xfu) == 0xfu) continue;
+        uint32_t xw[D];
 #pragma unroll
-    for (int j = 0; j < D; ++j) S ^= x[j];
-    uint32_t om[D];
+        for (int j = 0; j < D; ++j) xw[j] = x[j].w[q];
+        check_word<D, AMIN, HLIM>(xw, skip >> (4 * q), tb);
 #pragma unroll
-    for (int j = 0; j < D; ++j) om[j] = 0;
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-        int a[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) a[j] = abs((int)(int8_t)(x[j] >> (8 * f)));
-        int amin = a[0], arg = 0;                    // first minimum (min_by_key)
-#pragma unroll
-        for (int j = 1; j < D; ++j)
-            if (a[j] < amin) { amin = a[j]; arg = j; }
-        int delta = -1;
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            if (j != arg) delta = delta < 0 ? a[j] : hop(a[j], delta, negT);
-        }
-        int d2 = hop(delta, amin, negT);
-        if (HLIM) { delta = hardlimit(delta); d2 = hardlimit(d2); }
-#pragma unroll
-        for (int j = 0; j < D; ++j) om[j] |= (uint32_t)(j == arg ? delta : d2) << (8 * f);
+        for (int j = 0; j < D; ++j) x[j].w[q] = xw[j];
     }
 #pragma unroll
-    for (int j = 0; j < D; ++j) st_stream(mrow + j * kLanes, apply_signs(om[j], (S ^ x[j]) & 0x80808080u));
+    for (int j = 0; j < D; ++j) st_lane<NW>(msg, e0 + j, lane, x[j]);
 }
 
-// any degree up to kMaxGenericD; inputs staged in local memory
-template <bool AMIN, bool HLIM>
-__device__ __noinline__ void check_generic(uint32_t* __restrict__ mrow, int d, const int8_t* __restrict__ negT) {
-    uint32_t x[kMaxGenericD], om[kMaxGenericD];
-    uint32_t S = 0;
-    for (int j = 0; j < d; ++j) { x[j] = ld_stream(mrow + j * kLanes); S ^= x[j]; om[j] = 0; }
-    for (int f = 0; f < 4; ++f) {
-        if (AMIN) {
-            int amin = 1 << 20, arg = 0;
-            for (int j = 0; j < d; ++j) {
-                int a = abs((int)(int8_t)(x[j] >> (8 * f)));
-                if (a < amin) { amin = a; arg = j; }
-            }
-            int delta = -1;
-            for (int j = 0; j < d; ++j) {
-                if (j == arg) continue;
-                int a = abs((int)(int8_t)(x[j] >> (8 * f)));
-                delta = delta < 0 ? a : hop(a, delta, negT);
-            }
-            int d2 = hop(delta, amin, negT);
-            if (HLIM) { delta = hardlimit(delta); d2 = hardlimit(d2); }
-            for (int j = 0; j < d; ++j) om[j] |= (uint32_t)(j == arg ? delta : d2) << (8 * f);
-        } else {
-            int P = 0;
-            for (int j = 0; j < d; ++j) {
-                int acc = -1;
-                if (j > 0) acc = P;
-                for (int i = j + 1; i < d; ++i) {
-                    int a = abs((int)(int8_t)(x[i] >> (8 * f)));
-                    acc = acc < 0 ? a : gop(a, acc, negT);
+// any degree up to kMaxGenericD; one word at a time, inputs staged in local memory
+template <int NW, bool AMIN, bool HLIM>
+__device__ __noinline__ void check_generic(uint32_t* __restrict__ msg, size_t e0, int d, int lane, uint32_t skip, const Tables& tb) {
+    for (int q = 0; q < NW; ++q) {
+        uint32_t x[kMaxGenericD], om[kMaxGenericD];
+        uint32_t S = 0;
+        uint32_t* mrow = msg + (e0 * kLanes + lane) * NW + q;
+        for (int j = 0; j < d; ++j) { x[j] = __ldcg(mrow + (size_t)j * kLanes * NW); S ^= x[j]; om[j] = 0; }
+        for (int f = 0; f < 4; ++f) {
+            if (skip >> (4 * q + f) & 1) continue;
+            if (AMIN) {
+                int amin = 1 << 20, arg = 0;
+                for (int j = 0; j < d; ++j) {
+                    int a = mag_of(x[j], f);
+                    if (a < amin) { amin = a; arg = j; }
                 }
-                int mg = HLIM ? hardlimit(acc) : acc;
-                om[j] |= (uint32_t)mg << (8 * f);
-                int aj = abs((int)(int8_t)(x[j] >> (8 * f)));
-                P = j == 0 ? aj : gop(aj, P, negT);
+                int delta = -1;
+                for (int j = 0; j < d; ++j) {
+                    if (j == arg) continue;
+                    int a = mag_of(x[j], f);
+                    delta = delta < 0 ? a : hop(a, delta, tb);
+                }
+                int d2 = hop(delta, amin, tb);
+                if (HLIM) { delta = hardlimit(delta); d2 = hardlimit(d2); }
+                for (int j = 0; j < d; ++j) om[j] |= (uint32_t)(j == arg ? delta : d2) << (8 * f);
+            } else {
+                int P = 0;
+                for (int j = 0; j < d; ++j) {
+                    int acc = -1;
+                    if (j > 0) acc = P;
+                    for (int i = j + 1; i < d; ++i) {
+                        int a = mag_of(x[i], f);
+                        acc = acc < 0 ? a : gop(a, acc, tb);
+                    }
+                    int mg = HLIM ? hardlimit(acc) : acc;
+                    om[j] |= (uint32_t)mg << (8 * f);
+                    int aj = mag_of(x[j], f);
+                    P = j == 0 ? aj : gop(aj, P, tb);
+                }
             }
         }
-    }
-    for (int j = 0; j < d; ++j) st_stream(mrow + j * kLanes, apply_signs(om[j], (S ^ x[j]) & 0x80808080u));
-}
-
-template <bool AMIN, bool HLIM, int D>
-__device__ __forceinline__ void check_fixed(uint32_t* mrow, const int8_t* negT) {
-    if (AMIN) check_aminstar<D, HLIM>(mrow, negT);
-    else check_minstar<D, HLIM>(mrow, negT);
-}
-
-template <bool AMIN, bool HLIM>
-__device__ __forceinline__ void check_dispatch(uint32_t* mrow, int d, const int8_t* negT) {
-    switch (d) {
-        case 0: break;
-        case 1: break;   // the reference panics; such graphs are refused before launch
-        case 2: check_fixed<AMIN, HLIM, 2>(mrow, negT); break;
-        case 3: check_fixed<AMIN, HLIM, 3>(mrow, negT); break;
-        case 4: check_fixed<AMIN, HLIM, 4>(mrow, negT); break;
-        case 5: check_fixed<AMIN, HLIM, 5>(mrow, negT); break;
-        case 6: check_fixed<AMIN, HLIM, 6>(mrow, negT); break;
-        case 7: check_fixed<AMIN, HLIM, 7>(mrow, negT); break;
-        case 8: check_fixed<AMIN, HLIM, 8>(mrow, negT); break;
-        case 9: check_fixed<AMIN, HLIM, 9>(mrow, negT); break;
-        case 10: check_fixed<AMIN, HLIM, 10>(mrow, negT); break;
-        default: check_generic<AMIN, HLIM>(mrow, d, negT); break;
+        for (int j = 0; j < d; ++j) __stcg(mrow + (size_t)j * kLanes * NW, apply_signs(om[j], (S ^ x[j]) & 0x80808080u));
     }
 }
 
-// ---- variable node, arithmetic.rs:622-654, on 2 x (2 frames as s16x2) per lane -----------------
+// ---- variable node, arithmetic.rs:622-654, on 2 x (2 frames as s16x2) per word -----------------
 // Everything is kept in a biased unsigned domain (value + 128 per term) so that plain 32-bit adds
 // never carry between the two 16-bit halves; the bias is removed inside the DPX add-min op.
 struct VarAcc { uint32_t lo, hi; };
@@ -228,167 +241,288 @@ __device__ __forceinline__ uint32_t clip127(uint32_t v) {      // per-half clamp
     return __vmaxs2(__vmins2(v, 0x007f007fu), 0xff81ff81u);
 }
 
-// Finishes a variable node once the biased sum (input + all check messages) is known.
-// Returns the 4 hard bits; out(j, word) is called with the int8x4 message for slot j.
-template <class GetMsg, class PutMsg>
-__device__ __forceinline__ uint32_t var_finish(VarAcc sum, int d, bool jones, GetMsg get, PutMsg put) {
-    // true L = sum - 128*(d+1)
-    uint32_t Llo = __vadd2(sum.lo, rep16(-128 * (d + 1)));
-    uint32_t Lhi = __vadd2(sum.hi, rep16(-128 * (d + 1)));
-    uint32_t base_lo, base_hi, negK;
-    if (jones) {                                      // arithmetic.rs:806-810: L = clip(L)
+struct VarConsts { uint32_t negL, negK; bool jones; };
+__device__ __forceinline__ VarConsts var_consts(int d, bool jones) {
+    return {rep16(-128 * (d + 1)), jones ? rep16(-256) : rep16(-128 * d), jones};
+}
+
+// One word of a variable node once its biased sum (input + all check messages) is known: returns
+// the 4 hard bits and leaves in (base_lo, base_hi) the minuend for the outgoing messages.
+__device__ __forceinline__ uint32_t var_posterior(VarAcc sum, const VarConsts& k, uint32_t& base_lo, uint32_t& base_hi) {
+    uint32_t Llo = __vadd2(sum.lo, k.negL), Lhi = __vadd2(sum.hi, k.negL);   // true L = sum - 128*(d+1)
+    if (k.jones) {                                    // arithmetic.rs:806-810: L = clip(L)
         Llo = clip127(Llo);
         Lhi = clip127(Lhi);
         base_lo = __vadd2(Llo, rep16(384));           // L + 128 + 256 >= 257 > any biased message
         base_hi = __vadd2(Lhi, rep16(384));
-        negK = rep16(-256);
     } else {
         base_lo = sum.lo;
         base_hi = sum.hi;
-        negK = rep16(-128 * d);
-    }
-    for (int j = 0; j < d; ++j) {
-        VarAcc c = widen_biased(get(j));
-        // clip(L - c_j) = clamp((base - c'_j) - K, -127, 127); base >= c'_j in both halves
-        uint32_t vlo = __vmaxs2(__viaddmin_s16x2(base_lo - c.lo, negK, 0x007f007fu), 0xff81ff81u);
-        uint32_t vhi = __vmaxs2(__viaddmin_s16x2(base_hi - c.hi, negK, 0x007f007fu), 0xff81ff81u);
-        put(j, prmt(vlo, vhi, 0x6420));
     }
     // hard decision L <= 0  <=>  sign bit of (L - 1); clip() never changes it
     uint32_t zlo = __vadd2(Llo, 0xffffffffu), zhi = __vadd2(Lhi, 0xffffffffu);
-    uint32_t sb = prmt(zlo, zhi, 0x7531);             // high bytes of the four halves
-    return pack_bits4((sb >> 7) & 0x01010101u);
+    return pack_bits4((prmt(zlo, zhi, 0x7531) >> 7) & 0x01010101u);
 }
 
-template <int D>
-__device__ __forceinline__ uint32_t var_fixed(uint32_t* __restrict__ msg, const int* __restrict__ ce, uint32_t inw,
-                                              bool jones, bool deg1clip, int lane) {
-    uint32_t w[D];
-    int e[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) e[j] = __ldg(ce + j);
-#pragma unroll
-    for (int j = 0; j < D; ++j) w[j] = ld_stream(msg + (size_t)e[j] * kLanes + lane);
-    VarAcc sum = widen_biased(inw);
-    if (D == 1 && deg1clip) {                         // arithmetic.rs:826-842, biased: [12, 244]
-        sum.lo = __vmaxu2(__vminu2(sum.lo, rep16(244)), rep16(12));
-        sum.hi = __vmaxu2(__vminu2(sum.hi, rep16(244)), rep16(12));
-    }
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-        VarAcc c = widen_biased(w[j]);
-        sum.lo += c.lo;
-        sum.hi += c.hi;
-    }
-    return var_finish(sum, D, jones,
-                      [&](int j) { return w[j]; },
-                      [&](int j, uint32_t v) { st_stream(msg + (size_t)e[j] * kLanes + lane, v); });
+// clip(L - c_j) = clamp((base - c'_j) - K, -127, 127); base >= c'_j in both halves
+__device__ __forceinline__ uint32_t var_message(uint32_t c_i8x4, uint32_t base_lo, uint32_t base_hi, uint32_t negK) {
+    VarAcc c = widen_biased(c_i8x4);
+    uint32_t vlo = __vmaxs2(__viaddmin_s16x2(base_lo - c.lo, negK, 0x007f007fu), 0xff81ff81u);
+    uint32_t vhi = __vmaxs2(__viaddmin_s16x2(base_hi - c.hi, negK, 0x007f007fu), 0xff81ff81u);
+    return prmt(vlo, vhi, 0x6420);
 }
 
-__device__ __noinline__ uint32_t var_generic(uint32_t* __restrict__ msg, const int* __restrict__ ce, int d, uint32_t inw,
-                                             bool jones, int lane) {
-    VarAcc sum = widen_biased(inw);
-    for (int j = 0; j < d; ++j) {
-        VarAcc c = widen_biased(ld_stream(msg + (size_t)__ldg(ce + j) * kLanes + lane));
-        sum.lo += c.lo;
-        sum.hi += c.hi;
+// U variables of degree D per warp iteration: all index loads, then all message loads, then math
+template <int NW, int D, int U>
+__device__ __forceinline__ void var_class(uint32_t* __restrict__ msg, typename HBitsT<NW>::type* __restrict__ hbit,
+                                          const uint32_t* __restrict__ inq, const int* __restrict__ vlist,
+                                          const int* __restrict__ vedges, int count, bool jones, bool deg1clip,
+                                          uint32_t skip, int warp, int lane) {
+    const VarConsts k = var_consts(D, jones);
+    for (int i = warp * U; i < count; i += kWarps * U) {
+        int e[U][D];
+        Lane<NW> w[U][D], inw[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            ok[u] = i + u < count;
+            int ii = ok[u] ? i + u : i;
+            int v = __ldg(vlist + ii);
+#pragma unroll
+            for (int j = 0; j < D; ++j) e[u][j] = __ldg(vedges + (size_t)ii * D + j);
+            inw[u] = ld_lane<NW>(inq, (size_t)v, lane);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < D; ++j) w[u][j] = ld_lane<NW>(msg, (size_t)e[u][j], lane);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            uint32_t hb = 0;
+#pragma unroll
+            for (int q = 0; q < NW; ++q) {
+                if (((skip >> (4 * q)) & 0xfu) == 0xfu) continue;
+                VarAcc sum = widen_biased(inw[u].w[q]);
+                if (D == 1 && deg1clip) {             // arithmetic.rs:826-842, biased: [12, 244]
+                    sum.lo = __vmaxu2(__vminu2(sum.lo, rep16(244)), rep16(12));
+                    sum.hi = __vmaxu2(__vminu2(sum.hi, rep16(244)), rep16(12));
+                }
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    VarAcc c = widen_biased(w[u][j].w[q]);
+                    sum.lo += c.lo;
+                    sum.hi += c.hi;
+                }
+                uint32_t blo, bhi;
+                hb |= var_posterior(sum, k, blo, bhi) << (4 * q);
+#pragma unroll
+                for (int j = 0; j < D; ++j) w[u][j].w[q] = var_message(w[u][j].w[q], blo, bhi, k.negK);
+            }
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                st_lane<NW>(msg, (size_t)e[u][j], lane, w[u][j]);
+                hbit[(size_t)e[u][j] * kLanes + lane] = (typename HBitsT<NW>::type)hb;
+            }
+        }
     }
-    return var_finish(sum, d, jones,
-                      [&](int j) { return ld_stream(msg + (size_t)__ldg(ce + j) * kLanes + lane); },
-                      [&](int j, uint32_t v) { st_stream(msg + (size_t)__ldg(ce + j) * kLanes + lane, v); });
 }
 
-template <bool AMIN, bool HLIM>
+// variables of any degree > 8 (listed in vlist; edges through col_ptr / col_edge)
+template <int NW>
+__device__ __noinline__ void var_generic_class(uint32_t* __restrict__ msg, typename HBitsT<NW>::type* __restrict__ hbit,
+                                               const uint32_t* __restrict__ inq, const DeviceGraph& g,
+                                               const int* __restrict__ vlist, int count, bool jones, int warp, int lane) {
+    for (int i = warp; i < count; i += kWarps) {
+        int v = __ldg(vlist + i);
+        int p0 = __ldg(g.col_ptr + v), d = __ldg(g.col_ptr + v + 1) - p0;
+        const int* ce = g.col_edge + p0;
+        const VarConsts k = var_consts(d, jones);
+        uint32_t hb = 0;
+        for (int q = 0; q < NW; ++q) {
+            VarAcc sum = widen_biased(__ldg(inq + ((size_t)v * kLanes + lane) * NW + q));
+            for (int j = 0; j < d; ++j) {
+                VarAcc c = widen_biased(__ldcg(msg + ((size_t)__ldg(ce + j) * kLanes + lane) * NW + q));
+                sum.lo += c.lo;
+                sum.hi += c.hi;
+            }
+            uint32_t blo, bhi;
+            hb |= var_posterior(sum, k, blo, bhi) << (4 * q);
+            for (int j = 0; j < d; ++j) {
+                uint32_t* pm = msg + ((size_t)__ldg(ce + j) * kLanes + lane) * NW + q;
+                __stcg(pm, var_message(__ldcg(pm), blo, bhi, k.negK));
+            }
+        }
+        for (int j = 0; j < d; ++j) hbit[(size_t)__ldg(ce + j) * kLanes + lane] = (typename HBitsT<NW>::type)hb;
+    }
+}
+
+template <int NW, bool AMIN, bool HLIM>
 __global__ void __launch_bounds__(kWarps * 32) flood_i8_kernel(FloodI8Params p) {
-    __shared__ __align__(128) int8_t negT[128];
+    using HB = typename HBitsT<NW>::type;
+    constexpr int MAXD = NW == 1 ? 10 : 8;          // check degrees with an unrolled register path
+    constexpr uint32_t kAll = NW == 1 ? 0xfu : 0xffffu;
+    constexpr int kFrames = kTileFrames * NW;
+    __shared__ __align__(128) Tables tb;
     __shared__ uint32_t s_unsat[kLanes];
     __shared__ uint32_t s_done[kLanes];
+    __shared__ uint32_t s_skip;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t tile = blockIdx.x;
     const DeviceGraph& g = p.g;
-    uint32_t* msg = p.msg + tile * (size_t)g.E * kLanes;
-    const uint32_t* inq = p.inq + tile * (size_t)g.n * kLanes;
-    uint8_t* hard = p.hard + tile * (size_t)g.n * kLanes;
-    uint8_t* fin = p.final_hard + tile * (size_t)g.n * kLanes;
-    int32_t* iters = p.iters + tile * kTileFrames;
+    uint32_t* msg = p.msg + tile * (size_t)g.E * kLanes * NW;
+    HB* hbit = static_cast<HB*>(p.hbit) + tile * (size_t)g.E * kLanes;
+    const uint32_t* inq = p.inq + tile * (size_t)g.n * kLanes * NW;
+    const HB* raw0 = static_cast<const HB*>(p.raw0) + tile * (size_t)g.n * kLanes;
+    HB* fin = static_cast<HB*>(p.final_hard) + tile * (size_t)g.n * kLanes;
+    int32_t* iters = p.iters + tile * kFrames;
 
-    if (threadIdx.x < 128) {
-        // T[t] = round(8 ln(1 + e^{-t/8})) = #{theta in {1,3,5,9,13,22} : t < theta}  
-        int t = threadIdx.x;
-        negT[t] = (int8_t)-((t < 1) + (t < 3) + (t < 5) + (t < 9) + (t < 13) + (t < 22));
+    for (int i = threadIdx.x; i < 255; i += blockDim.x) {
+        int d = i - 127;
+        tb.U[i] = (int8_t)(min(d, 0) - table_T(abs(d)));
     }
+    if (threadIdx.x < 128) tb.Tp[threadIdx.x] = (int8_t)table_T(threadIdx.x);
     if (threadIdx.x < kLanes) { s_unsat[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) s_skip = 0;
 
-    // flooding.rs:88-100: first variable messages are the quantised channel LLRs
+    // flooding.rs:88-100: first variable messages are the quantised channel LLRs; the
+    // "iteration 0" hard decisions are the raw LLR signs (flooding.rs:57)
     for (int v = warp; v < g.n; v += kWarps) {
-        uint32_t w = __ldg(inq + (size_t)v * kLanes + lane);
+        Lane<NW> w = ld_lane<NW>(inq, (size_t)v, lane);
+        HB hb = raw0[(size_t)v * kLanes + lane];
         int p0 = __ldg(g.col_ptr + v), p1 = __ldg(g.col_ptr + v + 1);
-        for (int q = p0; q < p1; ++q) st_stream(msg + (size_t)__ldg(g.col_edge + q) * kLanes + lane, w);
+        for (int q = p0; q < p1; ++q) {
+            size_t e = (size_t)__ldg(g.col_edge + q);
+            st_lane<NW>(msg, e, lane, w);
+            hbit[e * kLanes + lane] = hb;
+        }
     }
     __syncthreads();
 
     for (int it = 1;; ++it) {
         const bool last = it > p.max_iter;           // only the syndrome of iteration max_iter is left
+        const uint32_t skip = s_skip;                // frame slots in which every lane has stopped
         uint32_t synd = 0;
-        for (int c = warp; c < g.m; c += kWarps) {
-            int e0 = __ldg(g.row_ptr + c), d = __ldg(g.row_ptr + c + 1) - e0;
-            uint32_t hb = 0;
-            for (int j = 0; j < d; ++j) hb ^= hard[(size_t)__ldg(g.col_idx + e0 + j) * kLanes + lane];
-            synd |= hb;
-            if (!last) check_dispatch<AMIN, HLIM>(msg + (size_t)e0 * kLanes + lane, d, negT);
+        {
+            // software pipeline over this warp's checks: the loads of check c+kWarps are in flight
+            // while check c is being computed
+            Lane<NW> xn[MAXD] = {};
+            uint32_t hn[MAXD] = {};
+            int e0n = 0, dn = 0;
+            auto prefetch = [&](int c) {
+                e0n = __ldg(g.row_ptr + c);
+                dn = __ldg(g.row_ptr + c + 1) - e0n;
+#pragma unroll
+                for (int j = 0; j < MAXD; ++j) {
+                    hn[j] = 0;
+                    if (j < dn && dn <= MAXD) {
+                        hn[j] = hbit[(size_t)(e0n + j) * kLanes + lane];
+                        if (!last) xn[j] = ld_lane<NW>(msg, (size_t)(e0n + j), lane);
+                    }
+                }
+            };
+            int c = warp;
+            if (c < g.m) prefetch(c);
+            for (; c < g.m; c += kWarps) {
+                Lane<NW> x[MAXD];
+                uint32_t hb = 0;
+                const int e0 = e0n, d = dn;
+#pragma unroll
+                for (int j = 0; j < MAXD; ++j) { x[j] = xn[j]; hb ^= hn[j]; }
+                if (c + kWarps < g.m) prefetch(c + kWarps);
+                if (d > MAXD) {
+                    for (int j = 0; j < d; ++j) hb ^= hbit[(size_t)(e0 + j) * kLanes + lane];
+                    if (!last) check_generic<NW, AMIN, HLIM>(msg, (size_t)e0, d, lane, skip, tb);
+                } else if (!last) {
+                    switch (d) {
+                        case 2: check_fixed<NW, MAXD, 2, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
+                        case 3: check_fixed<NW, MAXD, 3, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
+                        case 4: check_fixed<NW, MAXD, 4, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
+                        case 5: check_fixed<NW, MAXD, 5, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
+                        case 6: check_fixed<NW, MAXD, 6, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
+                        case 7: check_fixed<NW, MAXD, 7, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
+                        case 8: check_fixed<NW, MAXD, 8, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
+                        case 9: if (MAXD >= 9) check_fixed<NW, MAXD, (MAXD >= 9 ? 9 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
+                        case 10: if (MAXD >= 10) check_fixed<NW, MAXD, (MAXD >= 10 ? 10 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
+                        default: break;   // degree 0; degree 1 is refused before launch (reference panics)
+                    }
+                }
+                synd |= hb;
+            }
         }
         if (synd) atomicOr(&s_unsat[lane], synd);
         __syncthreads();
         const uint32_t unsat = s_unsat[lane], done = s_done[lane];
         // frames whose hard decisions of iteration it-1 satisfy every check stop now
         // (flooding.rs:57-64 for it-1 == 0, :69-79 otherwise)
-        uint32_t stop = ~unsat & ~done & 0xfu;
+        uint32_t stop = ~unsat & ~done & kAll;
         uint32_t fail = 0;
-        if (last) { fail = unsat & ~done & 0xfu; stop |= fail; }      // flooding.rs:81-85
+        if (last) { fail = unsat & ~done & kAll; stop |= fail; }      // flooding.rs:81-85
         const int any = __syncthreads_or(stop != 0);
         if (warp == 0) s_unsat[lane] = 0;
         if (any) {
             if (stop) {
                 for (int v = warp; v < g.n; v += kWarps) {
                     size_t o = (size_t)v * kLanes + lane;
-                    fin[o] = (uint8_t)((fin[o] & ~stop) | (hard[o] & stop));
+                    int p0 = __ldg(g.col_ptr + v), p1 = __ldg(g.col_ptr + v + 1);
+                    uint32_t hb;
+                    if (p1 > p0) hb = hbit[(size_t)__ldg(g.col_edge + p0) * kLanes + lane];
+                    else if (it == 1) hb = raw0[o];
+                    else {                            // isolated variable: posterior = quantised input
+                        hb = 0;
+                        for (int q = 0; q < NW; ++q) {
+                            uint32_t qw = __ldg(inq + o * NW + q);
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) hb |= (uint32_t)((int8_t)(qw >> (8 * b)) <= 0) << (4 * q + b);
+                        }
+                    }
+                    fin[o] = (HB)((fin[o] & ~stop) | (hb & stop));
                 }
             }
             if (warp == 0) {
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (stop >> b & 1) iters[lane * 4 + b] = (fail >> b & 1) ? -1 : it - 1;
+                for (int b = 0; b < 4 * NW; ++b)
+                    if (stop >> b & 1) iters[lane * 4 * NW + b] = (fail >> b & 1) ? -1 : it - 1;
                 s_done[lane] = done | stop;
+                uint32_t all_done = __reduce_and_sync(0xffffffffu, done | stop);
+                if (lane == 0) s_skip = all_done & kAll;
             }
         }
-        const int all = __syncthreads_and(((done | stop) & 0xfu) == 0xfu);
+        const int all = __syncthreads_and(((done | stop) & kAll) == kAll);
         if (all || last) break;
 
-        for (int v = warp; v < g.n; v += kWarps) {
-            int p0 = __ldg(g.col_ptr + v), d = __ldg(g.col_ptr + v + 1) - p0;
-            uint32_t inw = __ldg(inq + (size_t)v * kLanes + lane);
-            const int* ce = g.col_edge + p0;
-            uint32_t hb;
-            switch (d) {
-                case 0: {   // no checks: L = input (degree-one clip does not apply)
-                    VarAcc s = widen_biased(inw);
-                    hb = var_finish(s, 0, p.jones != 0, [&](int) { return 0u; }, [&](int, uint32_t) {});
-                    break;
-                }
-                case 1: hb = var_fixed<1>(msg, ce, inw, p.jones != 0, p.deg1clip != 0, lane); break;
-                case 2: hb = var_fixed<2>(msg, ce, inw, p.jones != 0, false, lane); break;
-                case 3: hb = var_fixed<3>(msg, ce, inw, p.jones != 0, false, lane); break;
-                case 4: hb = var_fixed<4>(msg, ce, inw, p.jones != 0, false, lane); break;
-                case 5: hb = var_fixed<5>(msg, ce, inw, p.jones != 0, false, lane); break;
-                case 6: hb = var_fixed<6>(msg, ce, inw, p.jones != 0, false, lane); break;
-                case 7: hb = var_fixed<7>(msg, ce, inw, p.jones != 0, false, lane); break;
-                case 8: hb = var_fixed<8>(msg, ce, inw, p.jones != 0, false, lane); break;
-                default: hb = var_generic(msg, ce, d, inw, p.jones != 0, lane); break;
+        const bool jones = p.jones != 0, d1c = p.deg1clip != 0;
+        const uint32_t vskip = s_skip;
+        for (int k = 0; k < p.vc.num_classes; ++k) {
+            const int deg = p.vc.deg[k], off = p.vc.off[k], cnt = p.vc.off[k + 1] - off;
+            const int* vl = p.vc.var_list + off;
+            const int* ve = p.vc.var_edges + p.vc.edge_off[k];
+            constexpr int U3 = NW == 1 ? 4 : 2, U8 = NW == 1 ? 2 : 1;
+            switch (deg) {
+                case 1: var_class<NW, 1, U3>(msg, hbit, inq, vl, ve, cnt, jones, d1c, vskip, warp, lane); break;
+                case 2: var_class<NW, 2, U3>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
+                case 3: var_class<NW, 3, U3>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
+                case 4: var_class<NW, 4, U8>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
+                case 5: var_class<NW, 5, U8>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
+                case 6: var_class<NW, 6, U8>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
+                case 7: var_class<NW, 7, U8>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
+                case 8: var_class<NW, 8, U8>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
+                default: var_generic_class<NW>(msg, hbit, inq, g, vl, cnt, jones, warp, lane); break;
             }
-            hard[(size_t)v * kLanes + lane] = (uint8_t)hb;
         }
         __syncthreads();
+    }
+}
+
+template <int NW>
+void launch_nw(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t stream) {
+    dim3 grid((unsigned)L.num_tiles), block(kWarps * 32);
+    if (L.aminstar) {
+        if (L.hardlimit) flood_i8_kernel<NW, true, true><<<grid, block, 0, stream>>>(p);
+        else flood_i8_kernel<NW, true, false><<<grid, block, 0, stream>>>(p);
+    } else {
+        if (L.hardlimit) flood_i8_kernel<NW, false, true><<<grid, block, 0, stream>>>(p);
+        else flood_i8_kernel<NW, false, false><<<grid, block, 0, stream>>>(p);
     }
 }
 
@@ -396,17 +530,11 @@ __global__ void __launch_bounds__(kWarps * 32) flood_i8_kernel(FloodI8Params p) 
 
 bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream) {
     FloodI8Params p;
-    p.g = L.graph;
-    p.msg = L.msg; p.inq = L.inq; p.hard = L.hard; p.final_hard = L.final_hard; p.iters = L.iters;
+    p.g = L.graph; p.vc = L.classes;
+    p.msg = L.msg; p.hbit = L.hbit; p.inq = L.inq; p.raw0 = L.raw0; p.final_hard = L.final_hard; p.iters = L.iters;
     p.max_iter = L.max_iter; p.jones = L.jones; p.deg1clip = L.deg1clip;
-    dim3 grid((unsigned)L.num_tiles), block(kWarps * 32);
-    if (L.aminstar) {
-        if (L.hardlimit) flood_i8_kernel<true, true><<<grid, block, 0, stream>>>(p);
-        else flood_i8_kernel<true, false><<<grid, block, 0, stream>>>(p);
-    } else {
-        if (L.hardlimit) flood_i8_kernel<false, true><<<grid, block, 0, stream>>>(p);
-        else flood_i8_kernel<false, false><<<grid, block, 0, stream>>>(p);
-    }
+    if (L.words_per_lane == 4) launch_nw<4>(L, p, stream);
+    else launch_nw<1>(L, p, stream);
     LDPC_CUDA_CHECK(cudaGetLastError());
     return true;
 }

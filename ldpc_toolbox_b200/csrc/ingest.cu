@@ -33,12 +33,15 @@ __device__ __forceinline__ int quantize_i8(float llr) {
     return (int)roundf(x);
 }
 
-template <typename TIn, int MODE>   // MODE 0: int8, 1: f32, 2: f64 decoder state
+// NW = words per lane of the decoder tile: a tile holds TF = 128*NW frames, stored per node as TF
+// consecutive values (frame index = lane*4*NW + word*4 + byte).
+template <typename TIn, int MODE, int NW>   // MODE 0: int8, 1: f32, 2: f64 decoder state
 __global__ void __launch_bounds__(kIngestWarps * 32) ingest_kernel(IngestLaunch p) {
-    __shared__ __align__(16) uint8_t s_q[MODE == 0 ? kChunk * 132 : 4];
-    __shared__ __align__(16) uint8_t s_raw[kChunk * 132];
-    __shared__ float s_f[MODE == 1 ? kChunk * 129 : 1];
-    __shared__ double s_d[MODE == 2 ? kChunk * 129 : 1];
+    constexpr int TF = kTileFrames * NW, ST = TF + 4;
+    __shared__ __align__(16) uint8_t s_q[MODE == 0 ? kChunk * ST : 4];
+    __shared__ __align__(16) uint8_t s_raw[kChunk * ST];
+    __shared__ float s_f[MODE == 1 ? kChunk * (TF + 1) : 1];
+    __shared__ double s_d[MODE == 2 ? kChunk * (TF + 1) : 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t tile = blockIdx.x;
@@ -47,56 +50,66 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_kernel(IngestLaunch 
     int src = -1;
     if (v < p.n) src = p.src_map ? __ldg(p.src_map + v) : v;
 
-    for (int fr = warp; fr < kTileFrames; fr += kIngestWarps) {
-        size_t frame = tile * kTileFrames + fr;
+    for (int fr = warp; fr < TF; fr += kIngestWarps) {
+        size_t frame = tile * TF + fr;
         TIn x = TIn(1);                                  // padding frames: clean all-zero codeword
         if (frame < p.nframes) x = src >= 0 ? llrs[frame * p.llrs_len + (size_t)src] : TIn(0);
-        s_raw[lane * 132 + fr] = x <= TIn(0) ? 1 : 0;
-        if (MODE == 0) s_q[lane * 132 + fr] = (uint8_t)(int8_t)quantize_i8(x);
-        if (MODE == 1) s_f[lane * 129 + fr] = (float)x;
-        if (MODE == 2) s_d[lane * 129 + fr] = (double)x;
+        s_raw[lane * ST + fr] = x <= TIn(0) ? 1 : 0;
+        if (MODE == 0) s_q[lane * ST + fr] = (uint8_t)(int8_t)quantize_i8(x);
+        if (MODE == 1) s_f[lane * (TF + 1) + fr] = (float)x;
+        if (MODE == 2) s_d[lane * (TF + 1) + fr] = (double)x;
     }
     __syncthreads();
     for (int vv = warp; vv < kChunk; vv += kIngestWarps) {
         if (v0 + vv >= p.n) break;
         size_t node = tile * (size_t)p.n + (size_t)(v0 + vv);
-        if (MODE == 0) p.inq_i8[node * kLanes + lane] = *reinterpret_cast<const uint32_t*>(&s_q[vv * 132 + lane * 4]);
+        if (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i)
+                p.inq_i8[node * (TF / 4) + i * 32 + lane] = *reinterpret_cast<const uint32_t*>(&s_q[vv * ST + (i * 32 + lane) * 4]);
+        }
         if (MODE == 1) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) p.in_f32[node * kTileFrames + i * 32 + lane] = s_f[vv * 129 + i * 32 + lane];
+            for (int i = 0; i < TF / 32; ++i) p.in_f32[node * TF + i * 32 + lane] = s_f[vv * (TF + 1) + i * 32 + lane];
         }
         if (MODE == 2) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) p.in_f64[node * kTileFrames + i * 32 + lane] = s_d[vv * 129 + i * 32 + lane];
+            for (int i = 0; i < TF / 32; ++i) p.in_f64[node * TF + i * 32 + lane] = s_d[vv * (TF + 1) + i * 32 + lane];
         }
-        p.hard[node * kLanes + lane] = (uint8_t)pack_bits4(*reinterpret_cast<const uint32_t*>(&s_raw[vv * 132 + lane * 4]));
+        uint32_t hb = 0;
+#pragma unroll
+        for (int q = 0; q < NW; ++q)
+            hb |= pack_bits4(*reinterpret_cast<const uint32_t*>(&s_raw[vv * ST + (lane * NW + q) * 4])) << (4 * q);
+        if (NW == 1) static_cast<uint8_t*>(p.hard)[node * kLanes + lane] = (uint8_t)hb;
+        else static_cast<uint16_t*>(p.hard)[node * kLanes + lane] = (uint16_t)hb;
     }
 }
 
-constexpr int kEmitChunk = 128;
+constexpr int kEmitChunk = 32;
 
+template <int NW>
 __global__ void __launch_bounds__(256) emit_kernel(EmitLaunch p) {
-    __shared__ uint8_t s[kTileFrames * 132];
+    constexpr int TF = kTileFrames * NW, ST = kEmitChunk + 4;
+    __shared__ uint8_t s[TF * ST];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t tile = blockIdx.x;
     const size_t v0 = (size_t)blockIdx.y * kEmitChunk;
     for (int vv = warp; vv < kEmitChunk; vv += 8) {
         size_t v = v0 + vv;
         uint32_t b = 0;
-        if (v < p.out_len) b = p.final_hard[(tile * (size_t)p.n + v) * kLanes + lane];
+        if (v < p.out_len) {
+            size_t o = (tile * (size_t)p.n + v) * kLanes + lane;
+            b = NW == 1 ? static_cast<const uint8_t*>(p.final_hard)[o] : static_cast<const uint16_t*>(p.final_hard)[o];
+        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s[(lane * 4 + k) * 132 + vv] = (b >> k) & 1;
+        for (int k = 0; k < 4 * NW; ++k) s[(lane * 4 * NW + k) * ST + vv] = (b >> k) & 1;
     }
     __syncthreads();
-    for (int fr = warp; fr < kTileFrames; fr += 8) {
-        size_t frame = tile * kTileFrames + fr;
+    for (int fr = warp; fr < TF; fr += 8) {
+        size_t frame = tile * TF + fr;
         if (frame >= p.nframes) break;
-        uint8_t* o = p.out + frame * p.out_stride;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            size_t v = v0 + i * 32 + lane;
-            if (v < p.out_len) o[v] = s[fr * 132 + i * 32 + lane];
-        }
+        size_t v = v0 + lane;
+        if (v < p.out_len) p.out[frame * p.out_stride + v] = s[fr * ST + lane];
     }
 }
 
@@ -106,14 +119,17 @@ bool launch_ingest(const IngestLaunch& L, cudaStream_t stream) {
     if (L.num_tiles == 0 || L.n == 0) return true;
     dim3 grid((unsigned)L.num_tiles, (unsigned)((L.n + kChunk - 1) / kChunk)), block(kIngestWarps * 32);
     const int mode = L.inq_i8 ? 0 : (L.in_f32 ? 1 : 2);
+    if (L.words_per_lane == 4 && mode != 0) { set_last_error("512-frame tiles are only used by the int8 decoders"); return false; }
     if (L.is_f64) {
-        if (mode == 0) ingest_kernel<double, 0><<<grid, block, 0, stream>>>(L);
-        else if (mode == 1) ingest_kernel<double, 1><<<grid, block, 0, stream>>>(L);
-        else ingest_kernel<double, 2><<<grid, block, 0, stream>>>(L);
+        if (mode == 0 && L.words_per_lane == 4) ingest_kernel<double, 0, 4><<<grid, block, 0, stream>>>(L);
+        else if (mode == 0) ingest_kernel<double, 0, 1><<<grid, block, 0, stream>>>(L);
+        else if (mode == 1) ingest_kernel<double, 1, 1><<<grid, block, 0, stream>>>(L);
+        else ingest_kernel<double, 2, 1><<<grid, block, 0, stream>>>(L);
     } else {
-        if (mode == 0) ingest_kernel<float, 0><<<grid, block, 0, stream>>>(L);
-        else if (mode == 1) ingest_kernel<float, 1><<<grid, block, 0, stream>>>(L);
-        else ingest_kernel<float, 2><<<grid, block, 0, stream>>>(L);
+        if (mode == 0 && L.words_per_lane == 4) ingest_kernel<float, 0, 4><<<grid, block, 0, stream>>>(L);
+        else if (mode == 0) ingest_kernel<float, 0, 1><<<grid, block, 0, stream>>>(L);
+        else if (mode == 1) ingest_kernel<float, 1, 1><<<grid, block, 0, stream>>>(L);
+        else ingest_kernel<float, 2, 1><<<grid, block, 0, stream>>>(L);
     }
     LDPC_CUDA_CHECK(cudaGetLastError());
     return true;
@@ -122,7 +138,8 @@ bool launch_ingest(const IngestLaunch& L, cudaStream_t stream) {
 bool launch_emit(const EmitLaunch& L, cudaStream_t stream) {
     if (L.num_tiles == 0 || L.out_len == 0) return true;
     dim3 grid((unsigned)L.num_tiles, (unsigned)((L.out_len + kEmitChunk - 1) / kEmitChunk)), block(256);
-    emit_kernel<<<grid, block, 0, stream>>>(L);
+    if (L.words_per_lane == 4) emit_kernel<4><<<grid, block, 0, stream>>>(L);
+    else emit_kernel<1><<<grid, block, 0, stream>>>(L);
     LDPC_CUDA_CHECK(cudaGetLastError());
     return true;
 }

@@ -64,6 +64,24 @@ def test_random_irregular_codes(oracle, impl):
         assert (its == -1).any() or (its > 0).any()
 
 
+@pytest.mark.parametrize("impl", ["Minstarapproxi8", "Aminstari8JonesPartialHardLimitDeg1Clip", "Minstarapproxi8JonesPartialHardLimit", "Aminstari8"])
+def test_512_frame_tiles(oracle, impl, monkeypatch):
+    """The 512-frame-tile kernel variant (4 words per lane), forced through LDPC_B200_NW."""
+    monkeypatch.setenv("LDPC_B200_NW", "4")
+    rng = np.random.default_rng(77)
+    for trial, (n, m) in enumerate([(96, 48), (150, 70)]):
+        alist = helpers.random_code_alist(rng, n, m, col_w=[1, 2, 3, 4, 9], extra_heavy_rows=trial * 2)
+        nframes = [700, 513][trial]
+        llrs = np.concatenate([helpers.awgn_llrs(rng, np.zeros((nframes // 4 + 1, n), dtype=np.uint8), s) for s in (0.3, 0.6, 0.9, 1.4)])[:nframes]
+        compare(oracle, alist, impl, llrs, 12, label=f"nw4 trial {trial} ")
+    alist = codes.alist_for("dvbs2:R1_2short")
+    enc = oracle.encoder(alist)
+    k = 16200 - 9000
+    msgs, cws = helpers.encoded_frames(enc, rng, k, 16200, 64)
+    llrs = helpers.awgn_llrs(rng, cws, helpers.sigma_for(1.0, k / 16200))
+    compare(oracle, alist, impl, llrs, 20, out_len=k, label="nw4 dvbs2 short ")
+
+
 def test_ragged_batch_and_strides(oracle):
     rng = np.random.default_rng(5)
     alist = helpers.random_code_alist(rng, 120, 60)
