@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "decoder_impl.hpp"
+#include "rules.cuh"
 
 namespace ldpc {
 
@@ -81,12 +82,11 @@ public:
                 if (d == 1 || (d == 0 && impl_.rule == Rule::Aminstar)) panics_ = true;
             }
         }
-        if (impl_.dtype == Dtype::I8 && impl_.schedule == Schedule::Flooding && g_.max_row_deg > flood_i8_max_row_degree()) {
-            set_last_error("row degree above the supported maximum of " + std::to_string(flood_i8_max_row_degree()));
-            return false;
-        }
-        if (impl_.dtype != Dtype::I8 || impl_.schedule != Schedule::Flooding) {
-            set_last_error("decoder implementation " + impl_.name + " is not available in this build yet");
+        kind_ = impl_.schedule == Schedule::HorizontalLayered ? Kind::Layered
+                : (impl_.dtype == Dtype::I8 ? Kind::FloodI8 : Kind::FloodFloat);
+        const int max_deg = kind_ == Kind::FloodI8 ? flood_i8_max_row_degree() : generic_max_row_degree();
+        if (g_.max_row_deg > max_deg) {
+            set_last_error("row degree above the supported maximum of " + std::to_string(max_deg));
             return false;
         }
         if (!d_row_ptr_.upload(g_.row_ptr) || !d_col_idx_.upload(g_.col_idx) || !d_col_ptr_.upload(g_.col_ptr) ||
@@ -94,7 +94,8 @@ public:
             return false;
         dg_.n = g_.n; dg_.m = g_.m; dg_.E = g_.E;
         dg_.row_ptr = d_row_ptr_.p; dg_.col_idx = d_col_idx_.p; dg_.col_ptr = d_col_ptr_.p; dg_.col_edge = d_col_edge_.p;
-        if (!build_var_classes()) return false;
+        if (kind_ == Kind::FloodI8 && !build_var_classes()) return false;
+        if (kind_ == Kind::Layered && !build_levels()) return false;
         LDPC_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
         for (auto& e : ev_) LDPC_CUDA_CHECK(cudaEventCreate(&e));
         max_tiles_opt_ = opt.max_tiles;
@@ -174,13 +175,20 @@ private:
 
     // words per lane for a batch: 512-frame tiles (512-byte HBM granules) once they can fill the GPU
     int pick_nw(size_t nframes) const {
+        if (kind_ != Kind::FloodI8) return 1;
         if (nw_opt_ == 1 || nw_opt_ == 4) return nw_opt_;
         return nframes >= (size_t)sm_count_ * 512 ? 4 : 1;
     }
 
     // HBM bytes of decoder state per 128 frames
+    size_t elem_size() const { return impl_.dtype == Dtype::F64 ? 8 : (impl_.dtype == Dtype::F32 ? 4 : 1); }
     size_t bytes_per_128() const {
-        return (size_t)g_.E * kLanes * 5 + (size_t)g_.n * kLanes * 4 + 2 * (size_t)g_.n * kLanes;
+        const size_t E = (size_t)g_.E, n = (size_t)g_.n;
+        if (kind_ == Kind::FloodI8) return E * kLanes * 5 + n * kLanes * 4 + 2 * n * kLanes;
+        const size_t s = elem_size();
+        if (kind_ == Kind::FloodFloat) return E * kTileFrames * s + E * kLanes + n * kTileFrames * s + 2 * n * kLanes;
+        const size_t qs = impl_.dtype == Dtype::I8 ? 2 : s;
+        return E * kTileFrames * s + n * kTileFrames * qs + 2 * n * kLanes;
     }
 
     // frames per kernel launch: whole waves of resident CTAs, bounded by free HBM
@@ -228,13 +236,43 @@ private:
         return true;
     }
 
+    // Level schedule for the layered kernels: rows that share no column commute, so a row only has
+    // to wait for the earlier rows it shares a column with (horizontal_layered.rs:105-110 order).
+    bool build_levels() {
+        std::vector<int> col_level((size_t)g_.n, 0), row_level((size_t)g_.m, 0);
+        int num_levels = 0;
+        for (int r = 0; r < g_.m; ++r) {
+            int lv = 0;
+            for (int q = g_.row_ptr[(size_t)r]; q < g_.row_ptr[(size_t)r + 1]; ++q) lv = std::max(lv, col_level[(size_t)g_.col_idx[(size_t)q]]);
+            row_level[(size_t)r] = lv;
+            for (int q = g_.row_ptr[(size_t)r]; q < g_.row_ptr[(size_t)r + 1]; ++q) col_level[(size_t)g_.col_idx[(size_t)q]] = lv + 1;
+            num_levels = std::max(num_levels, lv + 1);
+        }
+        std::vector<int> level_ptr((size_t)num_levels + 1, 0), level_rows((size_t)g_.m);
+        for (int r = 0; r < g_.m; ++r) level_ptr[(size_t)row_level[(size_t)r] + 1]++;
+        for (int l = 0; l < num_levels; ++l) level_ptr[(size_t)l + 1] += level_ptr[(size_t)l];
+        std::vector<int> fill(level_ptr.begin(), level_ptr.end() - 1);
+        for (int r = 0; r < g_.m; ++r) level_rows[(size_t)fill[(size_t)row_level[(size_t)r]]++] = r;
+        num_levels_ = num_levels;
+        return d_level_ptr_.upload(level_ptr) && d_level_rows_.upload(level_rows);
+    }
+
     bool ensure_workspace(size_t tiles, int nw) {
-        const size_t hb = nw == 4 ? 2 : 1;
-        if (!d_msg_.ensure(tiles * g_.E * kLanes * nw) || !d_hbit_.ensure(std::max<size_t>(tiles * g_.E * kLanes * hb, 1)) ||
-            !d_inq_.ensure(tiles * g_.n * kLanes * nw) || !d_hard_.ensure(tiles * g_.n * kLanes * hb) ||
-            !d_final_.ensure(tiles * g_.n * kLanes * hb))
+        const size_t E = (size_t)g_.E, n = (size_t)g_.n;
+        size_t msg_b, hbit_b, in_b, bits_b;
+        if (kind_ == Kind::FloodI8) {
+            const size_t hb = nw == 4 ? 2 : 1;
+            msg_b = tiles * E * kLanes * nw * 4; hbit_b = tiles * E * kLanes * hb; in_b = tiles * n * kLanes * nw * 4; bits_b = tiles * n * kLanes * hb;
+        } else if (kind_ == Kind::FloodFloat) {
+            msg_b = tiles * E * kTileFrames * elem_size(); hbit_b = tiles * E * kLanes; in_b = tiles * n * kTileFrames * elem_size(); bits_b = tiles * n * kLanes;
+        } else {
+            const size_t qs = impl_.dtype == Dtype::I8 ? 2 : elem_size();
+            msg_b = tiles * E * kTileFrames * elem_size(); hbit_b = 1; in_b = tiles * n * kTileFrames * qs; bits_b = tiles * n * kLanes;
+        }
+        if (!d_msg_.ensure(std::max<size_t>(msg_b, 1)) || !d_hbit_.ensure(std::max<size_t>(hbit_b, 1)) || !d_inq_.ensure(std::max<size_t>(in_b, 1)) ||
+            !d_hard_.ensure(std::max<size_t>(bits_b, 1)) || !d_final_.ensure(std::max<size_t>(bits_b, 1)))
             return false;
-        ws_bytes_ = (d_msg_.count + d_inq_.count) * 4 + d_hbit_.count + d_hard_.count + d_final_.count;
+        ws_bytes_ = d_msg_.count + d_inq_.count + d_hbit_.count + d_hard_.count + d_final_.count;
         return true;
     }
 
@@ -249,16 +287,32 @@ private:
         IngestLaunch in{};
         in.llrs = d_llrs; in.is_f64 = is_f64; in.llrs_len = llrs_len; in.nframes = nf; in.n = g_.n;
         in.src_map = punct_ ? d_src_map_.p : nullptr; in.num_tiles = tiles; in.words_per_lane = nw;
-        in.inq_i8 = d_inq_.p; in.hard = d_hard_.p;
+        in.hard = d_hard_.p;
+        if (kind_ == Kind::FloodI8) in.inq_i8 = reinterpret_cast<uint32_t*>(d_inq_.p);
+        else if (impl_.dtype == Dtype::F32) in.in_f32 = reinterpret_cast<float*>(d_inq_.p);
+        else if (impl_.dtype == Dtype::F64) in.in_f64 = reinterpret_cast<double*>(d_inq_.p);
+        else in.in_i16 = reinterpret_cast<int16_t*>(d_inq_.p);
         if (!launch_ingest(in, s)) return false;
         cudaEventRecord(ev_[1], s);
-        FloodI8Launch fl{};
-        fl.graph = dg_; fl.classes = vc_; fl.num_tiles = tiles; fl.words_per_lane = nw; fl.msg = d_msg_.p; fl.hbit = d_hbit_.p; fl.inq = d_inq_.p; fl.raw0 = d_hard_.p;
-        fl.final_hard = d_final_.p; fl.iters = d_iters_tile_.p;
         // a graph the min* rules panic on: run only the pre-check; everything else reports -2
-        fl.max_iter = panics_ ? 0 : (int)std::min<uint32_t>(max_it, 0x7ffffff0u);
-        fl.aminstar = impl_.rule == Rule::Aminstar; fl.jones = impl_.jones; fl.hardlimit = impl_.hardlimit; fl.deg1clip = impl_.deg1clip;
-        if (!launch_flood_i8(fl, s)) return false;
+        const int max_iter = panics_ ? 0 : (int)std::min<uint32_t>(max_it, 0x7ffffff0u);
+        if (kind_ == Kind::FloodI8) {
+            FloodI8Launch fl{};
+            fl.graph = dg_; fl.classes = vc_; fl.num_tiles = tiles; fl.words_per_lane = nw;
+            fl.msg = reinterpret_cast<uint32_t*>(d_msg_.p); fl.hbit = d_hbit_.p; fl.inq = reinterpret_cast<const uint32_t*>(d_inq_.p);
+            fl.raw0 = d_hard_.p; fl.final_hard = d_final_.p; fl.iters = d_iters_tile_.p; fl.max_iter = max_iter;
+            fl.aminstar = impl_.rule == Rule::Aminstar; fl.jones = impl_.jones; fl.hardlimit = impl_.hardlimit; fl.deg1clip = impl_.deg1clip;
+            if (!launch_flood_i8(fl, s)) return false;
+        } else {
+            GenericLaunch gl{};
+            gl.graph = dg_; gl.num_tiles = tiles; gl.is_f64 = impl_.dtype == Dtype::F64; gl.is_i8 = impl_.dtype == Dtype::I8;
+            gl.hardlimit = impl_.hardlimit;
+            gl.rule = impl_.rule == Rule::Phi ? kPhi : impl_.rule == Rule::Tanh ? kTanh : impl_.rule == Rule::Minstarapprox ? kMinstarapprox : kAminstar;
+            gl.msg = d_msg_.p; gl.hbit = d_hbit_.p; gl.in = d_inq_.p; gl.in_out_q = d_inq_.p;
+            gl.raw0 = d_hard_.p; gl.final_hard = d_final_.p; gl.iters = d_iters_tile_.p; gl.max_iter = max_iter;
+            gl.level_ptr = d_level_ptr_.p; gl.level_rows = d_level_rows_.p; gl.num_levels = num_levels_;
+            if (!(kind_ == Kind::FloodFloat ? launch_flood_float(gl, s) : launch_layered(gl, s))) return false;
+        }
         cudaEventRecord(ev_[2], s);
         EmitLaunch em{};
         em.final_hard = d_final_.p; em.n = g_.n; em.num_tiles = tiles; em.words_per_lane = nw; em.nframes = nf; em.out = d_out; em.out_len = out_len;
@@ -299,9 +353,12 @@ private:
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timed_ = false;
     BatchStats stats_;
-    DevBuf<int> d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_src_map_, d_var_list_, d_var_edges_;
+    enum class Kind { FloodI8, FloodFloat, Layered };
+    Kind kind_ = Kind::FloodI8;
+    DevBuf<int> d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_src_map_, d_var_list_, d_var_edges_, d_level_ptr_, d_level_rows_;
     VarClasses vc_{};
-    DevBuf<uint32_t> d_msg_, d_inq_;
+    int num_levels_ = 0;
+    DevBuf<uint8_t> d_msg_, d_inq_;
     DevBuf<uint8_t> d_hbit_, d_hard_, d_final_, d_stage_in_, d_stage_out_;
     DevBuf<int32_t> d_iters_tile_, d_stage_iters_;
 };

@@ -27,6 +27,7 @@ struct IngestLaunch {
     uint32_t* inq_i8;        // [tiles][n][32][NW] int8x4: quantised LLRs (arithmetic.rs:690-699)
     float* in_f32;           // [tiles][n][128] f32 (`llr as f32`)
     double* in_f64;          // [tiles][n][128] f64
+    int16_t* in_i16;         // [tiles][n][128] quantised LLRs widened to i16 (layered VarLlr, arithmetic.rs:709-711)
     void* hard;              // [tiles][n][32] raw-sign hard decisions (x <= 0.0), 4*NW bits per lane (u8 / u16)
 };
 bool launch_ingest(const IngestLaunch& L, cudaStream_t stream);
@@ -73,5 +74,27 @@ struct FloodI8Launch {
 };
 bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream);
 int flood_i8_max_row_degree();
+
+// ---- generic_bp.cu -----------------------------------------------------------------------------
+struct GenericLaunch {
+    DeviceGraph graph;
+    int num_tiles;
+    int rule;               // RuleId of rules.cuh
+    bool is_f64, is_i8, hardlimit;
+    void* msg;              // flooding: messages F [tiles][E][128]; layered: Rcv (F or int8) [tiles][E][128]
+    uint8_t* hbit;          // flooding only: [tiles][E][32]
+    const void* in;         // flooding: channel LLRs F [tiles][n][128]
+    void* in_out_q;         // layered: Qv (F or int16) [tiles][n][128], initialised by the ingest kernel
+    const uint8_t* raw0;    // [tiles][n][32]
+    uint8_t* final_hard;    // [tiles][n][32]
+    int32_t* iters;
+    int max_iter;
+    const int* level_ptr;   // layered: level schedule
+    const int* level_rows;
+    int num_levels;
+};
+bool launch_flood_float(const GenericLaunch& L, cudaStream_t stream);
+bool launch_layered(const GenericLaunch& L, cudaStream_t stream);
+int generic_max_row_degree();
 
 }  // namespace ldpc

@@ -35,12 +35,13 @@ __device__ __forceinline__ int quantize_i8(float llr) {
 
 // NW = words per lane of the decoder tile: a tile holds TF = 128*NW frames, stored per node as TF
 // consecutive values (frame index = lane*4*NW + word*4 + byte).
-template <typename TIn, int MODE, int NW>   // MODE 0: int8, 1: f32, 2: f64 decoder state
+template <typename TIn, int MODE, int NW>   // MODE 0: int8, 1: f32, 2: f64, 3: int16 decoder state
 __global__ void __launch_bounds__(kIngestWarps * 32) ingest_kernel(IngestLaunch p) {
     constexpr int TF = kTileFrames * NW, ST = TF + 4;
     __shared__ __align__(16) uint8_t s_q[MODE == 0 ? kChunk * ST : 4];
     __shared__ __align__(16) uint8_t s_raw[kChunk * ST];
     __shared__ float s_f[MODE == 1 ? kChunk * (TF + 1) : 1];
+    __shared__ int16_t s_h[MODE == 3 ? kChunk * (TF + 2) : 2];
     __shared__ double s_d[MODE == 2 ? kChunk * (TF + 1) : 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_kernel(IngestLaunch 
         if (MODE == 0) s_q[lane * ST + fr] = (uint8_t)(int8_t)quantize_i8(x);
         if (MODE == 1) s_f[lane * (TF + 1) + fr] = (float)x;
         if (MODE == 2) s_d[lane * (TF + 1) + fr] = (double)x;
+        if (MODE == 3) s_h[lane * (TF + 2) + fr] = (int16_t)quantize_i8(x);
     }
     __syncthreads();
     for (int vv = warp; vv < kChunk; vv += kIngestWarps) {
@@ -75,6 +77,10 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_kernel(IngestLaunch 
         if (MODE == 2) {
 #pragma unroll
             for (int i = 0; i < TF / 32; ++i) p.in_f64[node * TF + i * 32 + lane] = s_d[vv * (TF + 1) + i * 32 + lane];
+        }
+        if (MODE == 3) {
+#pragma unroll
+            for (int i = 0; i < TF / 32; ++i) p.in_i16[node * TF + i * 32 + lane] = s_h[vv * (TF + 2) + i * 32 + lane];
         }
         uint32_t hb = 0;
 #pragma unroll
@@ -118,18 +124,20 @@ __global__ void __launch_bounds__(256) emit_kernel(EmitLaunch p) {
 bool launch_ingest(const IngestLaunch& L, cudaStream_t stream) {
     if (L.num_tiles == 0 || L.n == 0) return true;
     dim3 grid((unsigned)L.num_tiles, (unsigned)((L.n + kChunk - 1) / kChunk)), block(kIngestWarps * 32);
-    const int mode = L.inq_i8 ? 0 : (L.in_f32 ? 1 : 2);
+    const int mode = L.inq_i8 ? 0 : (L.in_f32 ? 1 : (L.in_f64 ? 2 : 3));
     if (L.words_per_lane == 4 && mode != 0) { set_last_error("512-frame tiles are only used by the int8 decoders"); return false; }
     if (L.is_f64) {
         if (mode == 0 && L.words_per_lane == 4) ingest_kernel<double, 0, 4><<<grid, block, 0, stream>>>(L);
         else if (mode == 0) ingest_kernel<double, 0, 1><<<grid, block, 0, stream>>>(L);
         else if (mode == 1) ingest_kernel<double, 1, 1><<<grid, block, 0, stream>>>(L);
-        else ingest_kernel<double, 2, 1><<<grid, block, 0, stream>>>(L);
+        else if (mode == 2) ingest_kernel<double, 2, 1><<<grid, block, 0, stream>>>(L);
+        else ingest_kernel<double, 3, 1><<<grid, block, 0, stream>>>(L);
     } else {
         if (mode == 0 && L.words_per_lane == 4) ingest_kernel<float, 0, 4><<<grid, block, 0, stream>>>(L);
         else if (mode == 0) ingest_kernel<float, 0, 1><<<grid, block, 0, stream>>>(L);
         else if (mode == 1) ingest_kernel<float, 1, 1><<<grid, block, 0, stream>>>(L);
-        else ingest_kernel<float, 2, 1><<<grid, block, 0, stream>>>(L);
+        else if (mode == 2) ingest_kernel<float, 2, 1><<<grid, block, 0, stream>>>(L);
+        else ingest_kernel<float, 3, 1><<<grid, block, 0, stream>>>(L);
     }
     LDPC_CUDA_CHECK(cudaGetLastError());
     return true;
