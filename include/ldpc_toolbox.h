@@ -105,6 +105,30 @@ size_t ldpc_toolbox_decoder_llrs_len(void *decoder);       /* expected llrs_len 
  * returns the number of kernels launched by this handle so far */
 int64_t ldpc_toolbox_decoder_last_timing(void *decoder, float *ms3);
 
+/* On-device BER Monte-Carlo engine (BPSK/AWGN), the GPU counterpart of the reference's
+ * BerTest/Worker loop (reference src/simulation/ber.rs:246-282, :297-368, :436-481).
+ * ldpc_toolbox_ber_run simulates the global frames [first_frame, first_frame+nframes) at one
+ * Eb/N0 and ADDS to counters[9] = {frames, bit_errors, frame_errors, false_decodes,
+ * total_iterations, correct_iterations, bch_bit_errors, bch_frame_errors,
+ * bch_correct_iterations}.  Frames are keyed by their global index (Philox counter), so any
+ * sharding of the index range over calls or GPUs gives the same totals.  Returns 0 or -2. */
+void *ldpc_toolbox_ber_ctor(const char *alist, int alist_is_path, const char *implementation,
+                            const char *puncturing, int device, int max_tiles);
+void ldpc_toolbox_ber_dtor(void *ber);
+int32_t ldpc_toolbox_ber_run(void *ber, float ebn0_db, uint32_t max_iterations,
+                             uint64_t first_frame, uint64_t nframes, uint64_t seed,
+                             uint64_t bch_max_errors, uint64_t *counters);
+/* test hook: same as ldpc_toolbox_ber_run, also copying out (any pointer may be NULL) the f32
+ * LLRs [nframes][n_tx], decoded info bytes [nframes][k], iterations and packed messages */
+int32_t ldpc_toolbox_ber_run_dump(void *ber, float ebn0_db, uint32_t max_iterations,
+                                  uint64_t first_frame, uint64_t nframes, uint64_t seed,
+                                  uint64_t bch_max_errors, uint64_t *counters, float *llrs,
+                                  uint8_t *decoded, int32_t *iterations, uint32_t *messages);
+/* what[0]=k, [1]=N_cw, [2]=N (transmitted symbols per frame) */
+void ldpc_toolbox_ber_dims(void *ber, uint64_t *what3);
+double ldpc_toolbox_ber_rate(void *ber);                       /* k / N, ber.rs:259 */
+double ldpc_toolbox_ber_noise_sigma(void *ber, float ebn0_db); /* ber.rs:300-302 */
+
 int32_t ldpc_toolbox_num_implementations(void);
 const char *ldpc_toolbox_implementation_name(int32_t index);
 

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libldpc_toolbox.so")
 
-CU_SOURCES = ["capi.cu", "decoder.cu", "flood_i8.cu", "generic_bp.cu", "ingest.cu"]
+CU_SOURCES = ["ber.cu", "capi.cu", "decoder.cu", "flood_i8.cu", "generic_bp.cu", "ingest.cu"]
 CPP_SOURCES = ["host.cpp"]
 
 NVCC_FLAGS = [

@@ -33,6 +33,14 @@ _SIGS = {
     "ldpc_toolbox_decoder_num_edges": (C.c_size_t, [C.c_void_p]),
     "ldpc_toolbox_decoder_llrs_len": (C.c_size_t, [C.c_void_p]),
     "ldpc_toolbox_decoder_last_timing": (C.c_int64, [C.c_void_p, C.c_void_p]),
+    "ldpc_toolbox_ber_ctor": (C.c_void_p, [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int]),
+    "ldpc_toolbox_ber_dtor": (None, [C.c_void_p]),
+    "ldpc_toolbox_ber_run": (C.c_int32, [C.c_void_p, C.c_float, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "ldpc_toolbox_ber_run_dump": (C.c_int32, [C.c_void_p, C.c_float, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ldpc_toolbox_ber_dims": (None, [C.c_void_p, C.c_void_p]),
+    "ldpc_toolbox_ber_rate": (C.c_double, [C.c_void_p]),
+    "ldpc_toolbox_ber_noise_sigma": (C.c_double, [C.c_void_p, C.c_float]),
     "ldpc_toolbox_num_implementations": (C.c_int32, []),
     "ldpc_toolbox_implementation_name": (C.c_char_p, [C.c_int32]),
 }

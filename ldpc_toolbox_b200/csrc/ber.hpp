@@ -1,0 +1,53 @@
+// ldpc_toolbox_b200/csrc/ber.hpp — on-device BER Monte-Carlo engine (one Eb/N0 point at a time).
+// Mirrors BerTest / Worker of the reference (src/simulation/ber.rs:246-282, :297-368, :436-481):
+// the host keeps the stop rule and the statistics, the device does everything per frame.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+
+#include "decoder.hpp"
+#include "host.hpp"
+
+namespace ldpc {
+
+// counters: frames, bit_errors, frame_errors, false_decodes, total_iterations, correct_iterations,
+//           bch_bit_errors, bch_frame_errors, bch_correct_iterations          (ber.rs:313-337)
+constexpr int kBerCounters = 9;
+
+class BerEngine {
+public:
+    static std::unique_ptr<BerEngine> create(const Graph& g, const DecoderImplementation& impl, const Puncturer* punct,
+                                             const DecoderOptions& opt);
+    ~BerEngine();
+    // Simulates global frames [first_frame, first_frame + nframes) at ebn0_db and ADDS to counters[kBerCounters].
+    // Optional host dump buffers (test hooks): LLRs [nframes][n_tx] f32, decoded info bytes [nframes][k],
+    // iterations [nframes], messages [nframes][ceil(k/32)].
+    bool run(float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes, uint64_t seed,
+             uint64_t bch_max_errors, uint64_t* counters, float* dump_llrs = nullptr, uint8_t* dump_decoded = nullptr,
+             int32_t* dump_iters = nullptr, uint32_t* dump_messages = nullptr);
+    double noise_sigma(float ebn0_db) const;
+    int n() const { return n_; }
+    int k() const { return k_; }
+    int n_tx() const { return n_tx_; }       // transmitted symbols per frame ("Frame size (N)")
+    double rate() const { return rate_; }
+    long long kernel_launches() const { return launches_; }
+    LdpcDecoder* decoder() { return decoder_.get(); }
+
+private:
+    BerEngine() = default;
+    bool ensure(size_t nframes);
+    EncoderPlan plan_;
+    std::unique_ptr<LdpcDecoder> decoder_;
+    int n_ = 0, m_ = 0, k_ = 0, n_tx_ = 0, device_ = 0, g0_words_ = 0;
+    double rate_ = 0;
+    int* d_h0_ptr_ = nullptr; int* d_h0_idx_ = nullptr; uint32_t* d_g0_ = nullptr; int* d_kept_ = nullptr;
+    float* d_llrs_ = nullptr; uint32_t* d_messages_ = nullptr; uint8_t* d_decoded_ = nullptr; int32_t* d_iters_ = nullptr;
+    unsigned long long* d_counters_ = nullptr;
+    size_t cap_frames_ = 0;
+    cudaStream_t stream_ = nullptr;
+    long long launches_ = 0;
+};
+
+}  // namespace ldpc

@@ -6,6 +6,7 @@
 #include <sstream>
 
 #include "../../include/ldpc_toolbox.h"
+#include "ber.hpp"
 #include "decoder.hpp"
 #include "decoder_impl.hpp"
 
@@ -215,6 +216,49 @@ void ldpc_toolbox_encoder_encode(void* encoder, uint8_t* output, size_t output_l
     if (h->punctured) for (size_t i = 0; i < tx_len; ++i) output[i] = h->cw[(size_t)h->kept[i]];
     else memcpy(output, h->cw.data(), tx_len);
 }
+
+void* ldpc_toolbox_ber_ctor(const char* alist, int alist_is_path, const char* implementation, const char* puncturing, int device,
+                            int max_tiles) {
+    if (!alist || !implementation || !puncturing) return nullptr;
+    std::string text;
+    if (alist_is_path) { if (!slurp(alist, &text)) return nullptr; } else text = alist;
+    Graph g;
+    std::string err;
+    if (!Graph::from_alist(text, &g, &err)) { set_last_error(err); return nullptr; }
+    DecoderImplementation impl;
+    if (!DecoderImplementation::parse(implementation, &impl)) { set_last_error("invalid decoder implementation"); return nullptr; }
+    std::unique_ptr<Puncturer> p;
+    if (!make_puncturer(puncturing, &p)) return nullptr;
+    DecoderOptions opt;
+    opt.device = device;
+    opt.max_tiles = max_tiles;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { set_last_error("cudaSetDevice failed"); return nullptr; }
+    return BerEngine::create(g, impl, p.get(), opt).release();
+}
+
+void ldpc_toolbox_ber_dtor(void* ber) { delete static_cast<BerEngine*>(ber); }
+
+int32_t ldpc_toolbox_ber_run(void* ber, float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes, uint64_t seed,
+                             uint64_t bch_max_errors, uint64_t* counters) {
+    if (!ber || !counters) return -2;
+    return static_cast<BerEngine*>(ber)->run(ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors, counters) ? 0 : -2;
+}
+
+int32_t ldpc_toolbox_ber_run_dump(void* ber, float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes,
+                                  uint64_t seed, uint64_t bch_max_errors, uint64_t* counters, float* llrs, uint8_t* decoded,
+                                  int32_t* iterations, uint32_t* messages) {
+    if (!ber || !counters) return -2;
+    return static_cast<BerEngine*>(ber)->run(ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors, counters, llrs,
+                                             decoded, iterations, messages) ? 0 : -2;
+}
+
+void ldpc_toolbox_ber_dims(void* ber, uint64_t* what3) {
+    if (!ber || !what3) return;
+    auto* b = static_cast<BerEngine*>(ber);
+    what3[0] = (uint64_t)b->k(); what3[1] = (uint64_t)b->n(); what3[2] = (uint64_t)b->n_tx();
+}
+double ldpc_toolbox_ber_rate(void* ber) { return ber ? static_cast<BerEngine*>(ber)->rate() : 0.0; }
+double ldpc_toolbox_ber_noise_sigma(void* ber, float ebn0_db) { return ber ? static_cast<BerEngine*>(ber)->noise_sigma(ebn0_db) : 0.0; }
 
 const char* ldpc_toolbox_last_error(void) { return last_error().c_str(); }
 

@@ -1,0 +1,111 @@
+"""GPU tests of the on-device BER engine (K4/K5) through the C-ABI: the frames it generates are
+valid noisy codewords of the code, its counters equal a recount from dumped data with the CPU
+checker decoding the very same LLRs, results are invariant to sharding, the noise is Gaussian with
+the reference's sigma, and BER/FER agree statistically with the checker's own BER loop."""
+import math
+
+import numpy as np
+import pytest
+
+from ldpc_toolbox_b200 import codes
+from ldpc_toolbox_b200.ber import BerEngine, BerTest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("spec,impl,punct,ebn0", [
+    ("dvbs2:R1_2short", "Minstarapproxi8", "", 1.0),          # staircase encoder
+    ("ar4ja:1/2:1024", "Phif64", "1,1,1,1,0", 1.5),            # dense encoder + puncturing
+    ("nr5g:2:24", "HLAminstari8", "", 2.0),                    # dense encoder, layered decoder
+])
+def test_dump_consistency(oracle, spec, impl, punct, ebn0):
+    alist = codes.alist_for(spec)
+    eng = BerEngine(alist, impl, punct)
+    nframes, max_iter = 300, 20
+    counters, llrs, dec, its, msg = eng.run_dump(ebn0, max_iter, first_frame=1000, nframes=nframes)
+    # (1) the transmitted word is the systematic encoding of the message: noiseless part of the LLRs
+    enc = oracle.encoder(alist, punct)
+    sigma = eng.noise_sigma(ebn0)
+    tx = np.stack([enc.encode(m, eng.n) for m in msg])
+    y = llrs / (-2.0 / sigma**2)
+    noise = y - np.where(tx == 1, 1.0, -1.0)
+    assert abs(noise.mean()) < 5 * sigma / math.sqrt(noise.size)
+    assert abs(noise.std() / sigma - 1.0) < 0.01
+    assert abs((noise**4).mean() / sigma**4 - 3.0) < 0.1           # Gaussian kurtosis
+    assert abs(sigma - oracle.lib.ldpc_oracle_noise_sigma(eng.rate, 1.0, ebn0)) < 1e-12
+    # (2) the engine's decode of those LLRs = the checker's decode of the same LLRs
+    ref = oracle.decoder(alist, impl, punct)
+    rout, rits = ref.decode_batch(llrs, max_iter, out_len=eng.k)
+    if "i8" in impl:
+        assert (rits == its).all() and (rout == dec).all()
+    else:
+        assert ((rits != its) | (rout != dec).any(axis=1)).sum() <= 1
+    # (3) counters = recount (ber.rs:313-337)
+    be = (dec != msg).sum(axis=1)
+    iters = np.where(its < 0, max_iter, its)
+    assert counters["frames"] == nframes
+    assert counters["bit_errors"] == be.sum() and counters["frame_errors"] == (be > 0).sum()
+    assert counters["false_decodes"] == ((be > 0) & (its >= 0)).sum()
+    assert counters["total_iterations"] == iters.sum() and counters["correct_iterations"] == iters[be == 0].sum()
+    assert counters["bch_frame_errors"] == (be > 0).sum()            # bch_max_errors = 0
+    # messages look random
+    assert abs(msg.mean() - 0.5) < 5 * 0.5 / math.sqrt(msg.size)
+
+
+def test_sharding_invariance_and_determinism():
+    alist = codes.alist_for("dvbs2:R1_2short")
+    eng = BerEngine(alist, "Minstarapproxi8")
+    a = eng.run(1.0, 20, 0, 1000)
+    b = eng.run(1.0, 20, 0, 400)
+    eng.run(1.0, 20, 400, 600, counters=b)
+    assert (a == b).all()
+    c = BerEngine(alist, "Minstarapproxi8").run(1.0, 20, 0, 1000)
+    assert (a == c).all()
+    d = eng.run(1.0, 20, 0, 1000, seed=1)
+    assert (a != d).any()
+    e = eng.run(1.1, 20, 0, 1000)
+    assert (a != e).any()                                           # a different stream per Eb/N0
+    assert a[2] > 0 and a[2] < 1000
+
+
+def test_ber_statistical_parity_with_checker(oracle):
+    """FER of the GPU engine vs the CPU checker's BER loop on the same code/decoder/Eb/N0: each inside
+    the other's 3-sigma binomial band (the reference's RNG is OS-seeded, so only statistics compare)."""
+    alist = codes.alist_for("ar4ja:1/2:1024")
+    eng = BerEngine(alist, "Minstarapproxi8", "1,1,1,1,0")
+    for ebn0 in (1.0, 1.75):
+        g = eng.run(ebn0, 50, 0, 20000)
+        c = oracle.ber_run(alist, "Minstarapproxi8", "1,1,1,1,0", ebn0, 50, frames=4000, nthreads=0 or 8, seed=3)
+        pg, pc = g[2] / g[0], c["frame_errors"] / c["frames"]
+        s = math.sqrt(pc * (1 - pc) / c["frames"] + pg * (1 - pg) / g[0]) + 1e-9
+        assert abs(pg - pc) < 4 * s, (ebn0, pg, pc)
+        ig, ic = g[4] / g[0], c["total_iterations"] / c["frames"]
+        assert abs(ig - ic) < 0.05 * ic + 0.5, (ebn0, ig, ic)
+
+
+def test_ber_sweep_driver():
+    alist = codes.alist_for("dvbs2:R1_2short")
+    eng = BerEngine(alist, "Minstarapproxi8")
+    seen = []
+    t = BerTest([eng], eng.k, [0.6, 1.6], max_iterations=25, max_frame_errors=50, batch=2048, reporter=lambda st, fin: seen.append((st.ebn0_db, fin)))
+    stats = t.run()
+    assert [round(s.ebn0_db, 2) for s in stats] == [0.6, 1.6]
+    assert stats[0].ldpc.fer > 0.5 and stats[0].ldpc.frame_errors >= 50
+    assert stats[0].ldpc.ber > stats[0].ldpc.fer / eng.k
+    assert any(fin for _, fin in seen)
+    assert stats[0].throughput_mbps > 0
+
+
+def test_cli_ber_output(tmp_path, capsys):
+    from ldpc_toolbox_b200 import cli
+    p = tmp_path / "code.alist"
+    p.write_text(codes.alist_for("dvbs2:R1_2short"))
+    out = tmp_path / "out.txt"
+    cli.main(["ber", str(p), "--decoder", "Minstarapproxi8", "--min-ebn0", "0.5", "--max-ebn0", "0.75", "--step-ebn0", "0.25",
+              "--max-iter", "20", "--frame-errors", "20", "--batch", "1024", "--output-file", str(out)])
+    text = capsys.readouterr().out
+    assert "BER TEST PARAMETERS" in text and " - Information bits (k): 7200" in text and " - Code rate: 0.444" in text
+    assert " - Implementation: Minstarapproxi8" in text
+    rows = [l for l in out.read_text().split("\n") if l.startswith("   0.")]
+    assert len(rows) == 2 and rows[0].startswith("   0.50 |") and rows[1].startswith("   0.75 |")
+    assert rows[0].count("|") == 10

