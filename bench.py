@@ -174,11 +174,22 @@ def run_ours(args):
     achieved = alg / (bp_ms * 1e-3) / 1e9
 
     # ---- e2e: same metric through the public host-buffer call, H2D + D2H inside the timed region
-    e2e_frames = min(frames, args.e2e_tiles * 128)
-    h_llrs = torch.empty((e2e_frames, N), dtype=torch.float32).pin_memory()
-    h_llrs.copy_(llrs[:e2e_frames].cpu())
-    h_out = torch.empty((e2e_frames, K_INFO), dtype=torch.uint8).pin_memory()
-    h_it = torch.empty((e2e_frames,), dtype=torch.int32).pin_memory()
+    # two launch-sized chunks so the library can overlap H2D / kernels / D2H, if host RAM allows pinning them
+    e2e_frames = args.e2e_tiles * 128 if args.e2e_tiles > 0 else 2 * frames
+    try:
+        avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
+    except Exception:
+        avail = 0
+    while e2e_frames > 128 and e2e_frames * (N * 4 + K_INFO) > 0.25 * avail:    # pinned buffers stay below a quarter of host RAM (an 88 GB pin got the process OOM-killed)
+        e2e_frames //= 2
+    h_llrs = torch.empty((e2e_frames, N), dtype=torch.float32, pin_memory=True)
+    for f0 in range(0, e2e_frames, frames):
+        nf = min(frames, e2e_frames - f0)
+        h_llrs[f0:f0 + nf].copy_(llrs[:nf])
+    del llrs, out, iters                       # free HBM for the library's double-buffered staging
+    torch.cuda.empty_cache()
+    h_out = torch.empty((e2e_frames, K_INFO), dtype=torch.uint8, pin_memory=True)
+    h_it = torch.empty((e2e_frames,), dtype=torch.int32, pin_memory=True)
 
     def e2e_step():
         dec.decode_batch_ptr(h_llrs.data_ptr(), False, N, e2e_frames, MAX_ITER, h_out.data_ptr(), K_INFO, K_INFO, h_it.data_ptr(),
@@ -188,7 +199,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 2))
     for _ in range(e2e_steps):
         e2e_step()
     e2e_s = time.perf_counter() - t0
@@ -301,7 +312,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tiles", type=int, default=0, help="frames per GPU per step / 128 (default 8 per SM = two 512-frame tiles per SM)")
-    ap.add_argument("--e2e-tiles", type=int, default=148)
+    ap.add_argument("--e2e-tiles", type=int, default=0, help="frames of the end-to-end leg / 128 (default: two launches' worth)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--faithful-send", action="store_true", help="reference arm: time the linear-search send of decoder.rs:111-117")

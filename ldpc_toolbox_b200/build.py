@@ -20,10 +20,13 @@ LIB = os.path.join(OUT_DIR, "libldpc_toolbox.so")
 CU_SOURCES = ["ber.cu", "capi.cu", "decoder.cu", "flood_i8.cu", "generic_bp.cu", "ingest.cu"]
 CPP_SOURCES = ["host.cpp"]
 
+# experiment knobs for flood_i8.cu (warps per CTA, min CTAs per SM); empty = the defaults in the source
+EXTRA_DEFINES = [d for d in os.environ.get("LDPC_B200_DEFINES", "").split() if d]
+
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall", "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + EXTRA_DEFINES
 
 
 def _nvcc() -> str:

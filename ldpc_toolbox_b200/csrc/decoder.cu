@@ -54,7 +54,11 @@ public:
     GpuDecoder(const DecoderImplementation& impl, const Graph& g) : impl_(impl), g_(g) {}
     ~GpuDecoder() override {
         if (stream_) cudaStreamDestroy(stream_);
+        if (h2d_stream_) cudaStreamDestroy(h2d_stream_);
+        if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
         for (auto& e : ev_) if (e) cudaEventDestroy(e);
+        for (int b = 0; b < 2; ++b)
+            for (cudaEvent_t e : {ev_copied_[b], ev_ingested_[b], ev_emitted_[b], ev_drained_[b]}) if (e) cudaEventDestroy(e);
     }
 
     bool init(const Puncturer* punct, const DecoderOptions& opt) {
@@ -127,24 +131,50 @@ public:
         if (nframes == 0) return true;
         LDPC_CUDA_CHECK(cudaSetDevice(device_));
         const size_t esz = is_f64 ? 8 : 4;
-        const size_t chunk_frames = plan_chunk_frames(nframes);
+        // Chunks are pipelined: the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the
+        // kernels of chunk i (two staging buffers each way, copy engines on their own streams).
+        // Truly asynchronous only when the caller's buffers are pinned.
+        size_t chunk_frames = plan_chunk_frames(nframes, /*staging_bytes_per_frame=*/2 * (llrs_len * esz + out_len + 4));
+        const size_t nchunks = (nframes + chunk_frames - 1) / chunk_frames;
+        const int nbuf = nchunks > 1 ? 2 : 1;
         const size_t stage_frames = std::min(nframes, chunk_frames);
-        if (!d_stage_in_.ensure(stage_frames * llrs_len * esz) || !d_stage_out_.ensure(std::max<size_t>(stage_frames * out_len, 1)) ||
-            !d_stage_iters_.ensure(stage_frames))
-            return false;
-        for (size_t f0 = 0; f0 < nframes; f0 += chunk_frames) {
-            size_t nf = std::min(chunk_frames, nframes - f0);
-            LDPC_CUDA_CHECK(cudaMemcpyAsync(d_stage_in_.p, (const uint8_t*)llrs + f0 * llrs_len * esz, nf * llrs_len * esz,
-                                            cudaMemcpyHostToDevice, stream_));
-            if (!run_chunk(d_stage_in_.p, is_f64, llrs_len, nf, max_iterations, d_stage_out_.p, out_len, out_len,
-                           d_stage_iters_.p, stream_))
+        for (int b = 0; b < nbuf; ++b)
+            if (!d_stage_in_[b].ensure(stage_frames * llrs_len * esz) || !d_stage_out_[b].ensure(std::max<size_t>(stage_frames * out_len, 1)) ||
+                !d_stage_iters_[b].ensure(stage_frames))
                 return false;
-            if (out_len)
-                LDPC_CUDA_CHECK(cudaMemcpy2DAsync(out + f0 * out_stride, out_stride, d_stage_out_.p, out_len, out_len, nf,
-                                                  cudaMemcpyDeviceToHost, stream_));
-            LDPC_CUDA_CHECK(cudaMemcpyAsync(iterations + f0, d_stage_iters_.p, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
-            LDPC_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        if (!h2d_stream_) {
+            LDPC_CUDA_CHECK(cudaStreamCreateWithFlags(&h2d_stream_, cudaStreamNonBlocking));
+            LDPC_CUDA_CHECK(cudaStreamCreateWithFlags(&d2h_stream_, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) {
+                LDPC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_copied_[b], cudaEventDisableTiming));
+                LDPC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_ingested_[b], cudaEventDisableTiming));
+                LDPC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_emitted_[b], cudaEventDisableTiming));
+                LDPC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_drained_[b], cudaEventDisableTiming));
+            }
         }
+        size_t ci = 0;
+        for (size_t f0 = 0; f0 < nframes; f0 += chunk_frames, ++ci) {
+            const int b = (int)(ci % (size_t)nbuf);
+            const size_t nf = std::min(chunk_frames, nframes - f0);
+            if (ci >= (size_t)nbuf) LDPC_CUDA_CHECK(cudaStreamWaitEvent(h2d_stream_, ev_ingested_[b], 0));   // staging-in buffer consumed
+            LDPC_CUDA_CHECK(cudaMemcpyAsync(d_stage_in_[b].p, (const uint8_t*)llrs + f0 * llrs_len * esz, nf * llrs_len * esz,
+                                            cudaMemcpyHostToDevice, h2d_stream_));
+            LDPC_CUDA_CHECK(cudaEventRecord(ev_copied_[b], h2d_stream_));
+            LDPC_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_copied_[b], 0));
+            if (ci >= (size_t)nbuf) LDPC_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_drained_[b], 0));        // staging-out buffer drained
+            if (!run_chunk(d_stage_in_[b].p, is_f64, llrs_len, nf, max_iterations, d_stage_out_[b].p, out_len, out_len,
+                           d_stage_iters_[b].p, stream_, ev_ingested_[b]))
+                return false;
+            LDPC_CUDA_CHECK(cudaEventRecord(ev_emitted_[b], stream_));
+            LDPC_CUDA_CHECK(cudaStreamWaitEvent(d2h_stream_, ev_emitted_[b], 0));
+            if (out_len)
+                LDPC_CUDA_CHECK(cudaMemcpy2DAsync(out + f0 * out_stride, out_stride, d_stage_out_[b].p, out_len, out_len, nf,
+                                                  cudaMemcpyDeviceToHost, d2h_stream_));
+            LDPC_CUDA_CHECK(cudaMemcpyAsync(iterations + f0, d_stage_iters_[b].p, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, d2h_stream_));
+            LDPC_CUDA_CHECK(cudaEventRecord(ev_drained_[b], d2h_stream_));
+        }
+        LDPC_CUDA_CHECK(cudaStreamSynchronize(d2h_stream_));
+        LDPC_CUDA_CHECK(cudaStreamSynchronize(stream_));
         return true;
     }
 
@@ -155,7 +185,7 @@ public:
         if (nframes == 0) return true;
         LDPC_CUDA_CHECK(cudaSetDevice(device_));
         const size_t esz = is_f64 ? 8 : 4;
-        const size_t chunk_frames = plan_chunk_frames(nframes);
+        const size_t chunk_frames = plan_chunk_frames(nframes, 0);
         for (size_t f0 = 0; f0 < nframes; f0 += chunk_frames) {
             size_t nf = std::min(chunk_frames, nframes - f0);
             if (!run_chunk((const uint8_t*)d_llrs + f0 * llrs_len * esz, is_f64, llrs_len, nf, max_iterations,
@@ -192,18 +222,22 @@ private:
     }
 
     // frames per kernel launch: whole waves of resident CTAs, bounded by free HBM
-    size_t plan_chunk_frames(size_t nframes) {
-        const int nw = pick_nw(nframes);
-        const size_t tf = (size_t)kTileFrames * nw;
-        size_t need = (nframes + tf - 1) / tf;
-        size_t cap = max_tiles_opt_ > 0 ? std::max<size_t>((size_t)max_tiles_opt_ / nw, 1) : (size_t)sm_count_ * (nw == 4 ? 2 : 4);
+    size_t plan_chunk_frames(size_t nframes, size_t staging_bytes_per_frame) {
+        // cap in units of 128 frames: two 512-frame tiles (int8 flooding) or four 128-frame tiles per SM
+        size_t cap = max_tiles_opt_ > 0 ? (size_t)max_tiles_opt_ : (size_t)sm_count_ * (kind_ == Kind::FloodI8 ? 8 : 4);
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            size_t budget = (size_t)((double)(free_b + ws_bytes_) * 0.45);
-            size_t fit = std::max<size_t>(budget / std::max<size_t>(bytes_per_128() * nw, 1), 1);
+            size_t have = ws_bytes_ + d_stage_in_[0].count + d_stage_in_[1].count + d_stage_out_[0].count + d_stage_out_[1].count;
+            size_t budget = (size_t)((double)(free_b + have) * (staging_bytes_per_frame ? 0.85 : 0.45));
+            size_t fit = std::max<size_t>(budget / std::max<size_t>(bytes_per_128() + staging_bytes_per_frame * kTileFrames, 1), 1);
             cap = std::min(cap, fit);
         }
-        return std::max<size_t>(1, std::min(need, cap)) * tf;
+        const size_t need = (nframes + kTileFrames - 1) / kTileFrames;
+        size_t frames = std::max<size_t>(1, std::min(need, cap)) * kTileFrames;
+        const size_t tf = (size_t)kTileFrames * pick_nw(frames);
+        if (frames > tf) frames = frames / tf * tf;           // whole tiles per launch (the last chunk may be ragged)
+        else frames = tf;
+        return frames;
     }
 
     // variables bucketed by degree so the variable pass runs fixed-degree, unrolled code
@@ -277,7 +311,7 @@ private:
     }
 
     bool run_chunk(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
-                   size_t out_len, size_t out_stride, int32_t* d_iters, cudaStream_t s) {
+                   size_t out_len, size_t out_stride, int32_t* d_iters, cudaStream_t s, cudaEvent_t after_ingest = nullptr) {
         const int nw = pick_nw(nf);
         const size_t tf = (size_t)kTileFrames * nw;
         const int tiles = (int)((nf + tf - 1) / tf);
@@ -294,6 +328,7 @@ private:
         else in.in_i16 = reinterpret_cast<int16_t*>(d_inq_.p);
         if (!launch_ingest(in, s)) return false;
         cudaEventRecord(ev_[1], s);
+        if (after_ingest) cudaEventRecord(after_ingest, s);
         // a graph the min* rules panic on: run only the pre-check; everything else reports -2
         const int max_iter = panics_ ? 0 : (int)std::min<uint32_t>(max_it, 0x7ffffff0u);
         if (kind_ == Kind::FloodI8) {
@@ -359,8 +394,10 @@ private:
     VarClasses vc_{};
     int num_levels_ = 0;
     DevBuf<uint8_t> d_msg_, d_inq_;
-    DevBuf<uint8_t> d_hbit_, d_hard_, d_final_, d_stage_in_, d_stage_out_;
-    DevBuf<int32_t> d_iters_tile_, d_stage_iters_;
+    DevBuf<uint8_t> d_hbit_, d_hard_, d_final_, d_stage_in_[2], d_stage_out_[2];
+    DevBuf<int32_t> d_iters_tile_, d_stage_iters_[2];
+    cudaStream_t h2d_stream_ = nullptr, d2h_stream_ = nullptr;
+    cudaEvent_t ev_copied_[2] = {}, ev_ingested_[2] = {}, ev_emitted_[2] = {}, ev_drained_[2] = {};
 };
 
 __global__ void mark_panics_kernel(int32_t* iters, size_t nf) {

@@ -26,6 +26,15 @@
 //      g(a, acc) = max(0, acc + U[d]),   U[d] = min(d, 0) - T[|d|]
 // so one fold step is: subtract, one table read, one fused add-max(0) (VIADDMNMX.RELU).
 // U is a 255-entry int8 table in shared memory.
+//
+// Storage format: every int8 quantity in HBM (messages, channel LLRs) is kept in offset binary,
+// byte = value + 128 in [1, 255].  |v| of four frames is then ONE instruction (VABSDIFF4.U8 against
+// 0x80808080), the variable node's carry-free SWAR sums need no re-biasing, and signs travel in bit 7.
+//
+// Pipe balance: the kernel is bound by the integer ALU pipe (min/max, LOP3, PRMT, VIADDMNMX), while
+// the FMA pipe (IMAD) idles.  Plain adds/subtracts/shifts-and-ors on the critical path are therefore
+// written as mad.lo with a multiplier taken from a kernel parameter (ptxas cannot fold it), which
+// pins them to the FMA pipe: a fold step is IMAD + LDS + VIADDMNMX = one instruction per pipe.
 #include <string>
 
 #include "decoder_impl.hpp"
@@ -46,9 +55,19 @@ struct FloodI8Params {
     int32_t* iters;         // [tiles*128*NW]     iterations, or -1 on failure
     int max_iter;
     int jones, deg1clip;
+    // opaque multipliers for FMA-pipe integer arithmetic (see header): -1, 1, -2, 255, 2^8, 2^16, 2^24
+    int c_m1, c_one, c_m2, c_ff, c_sh8, c_sh16, c_sh24;
 };
 
-constexpr int kWarps = 8;            // warps per CTA
+struct Consts { int m1, one, m2, ff, sh[4]; };
+
+#ifndef LDPC_I8_WARPS
+#define LDPC_I8_WARPS 8
+#endif
+#ifndef LDPC_I8_MINBLOCKS
+#define LDPC_I8_MINBLOCKS 2
+#endif
+constexpr int kWarps = LDPC_I8_WARPS;            // warps per CTA
 constexpr int kMaxGenericD = 64;     // larger rows are rejected when the decoder is built
 
 template <int NW> struct Lane { uint32_t w[NW]; };
@@ -74,6 +93,13 @@ __device__ __forceinline__ void st_lane(uint32_t* base, size_t node, int lane, c
     else __stcg(p, v.w[0]);
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS), L2 only
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct Tables {
     int8_t U[256];      // U[d + 127], d = a - acc in [-127, 127]
     int8_t Tp[128];     // T[t]
@@ -84,45 +110,63 @@ __device__ __forceinline__ int table_T(int t) {
     return (t < 1) + (t < 3) + (t < 5) + (t < 9) + (t < 13) + (t < 22);
 }
 
-// g(a, acc) of arithmetic.rs:741 on non-negative ints
-__device__ __forceinline__ int gop(int a, int acc, const Tables& tb) {
-    return __viaddmax_s32_relu(acc, (int)tb.U[a - acc + 127], 0);
+// a*b + c on the FMA pipe (b must come from a kernel parameter so that it stays an IMAD)
+__device__ __forceinline__ int imad(int a, int b, int c) {
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// g(a, acc) of arithmetic.rs:741 on non-negative ints: IMAD (a - acc), LDS, VIADDMNMX.RELU
+__device__ __forceinline__ int gop(int a, int acc, const Tables& tb, const Consts& k) {
+    return __viaddmax_s32_relu(acc, (int)tb.U[imad(acc, k.m1, a) + 127], 0);
 }
 
 // h(a, acc) of arithmetic.rs:1155-1157
-__device__ __forceinline__ int hop(int a, int acc, const Tables& tb) {
+__device__ __forceinline__ int hop(int a, int acc, const Tables& tb, const Consts& k) {
     int s = min(a + acc, 127);                      // i8 saturating_add
-    return max(acc + (int)tb.U[a - acc + 127] + (int)tb.Tp[s], 0);
+    return max(acc + (int)tb.U[imad(acc, k.m1, a) + 127] + (int)tb.Tp[s], 0);
 }
 
 __device__ __forceinline__ int hardlimit(int mag) { return mag >= 100 ? 127 : mag; }   // arithmetic.rs:812-824
 
-// magnitude word (4 x 0..127) and sign word (bit 7 of each byte) -> 4 x int8 two's complement,
-// with -0 = 0
-__device__ __forceinline__ uint32_t apply_signs(uint32_t mag, uint32_t sgn) {
-    uint32_t m1 = sgn >> 7;
-    uint32_t m7 = sgn - m1;                          // 0x7f in negative bytes
-    return ((mag ^ m7) + m1) ^ sgn;
+// magnitude word (4 x 0..127) and sign word (0x80 in negative bytes) -> offset-binary bytes 128 +- mag
+__device__ __forceinline__ uint32_t apply_signs(uint32_t mag, uint32_t sgn, const Consts& k) {
+    uint32_t negmask = (uint32_t)imad((int)(sgn >> 7), k.ff, 0);        // 0xff in negative bytes
+    uint32_t t = mag & negmask;
+    return (uint32_t)imad((int)t, k.m2, (int)(mag + 0x80808080u));      // per byte: 128 + mag - 2*t, no borrows
 }
 
-__device__ __forceinline__ int mag_of(uint32_t x, int f) { return abs((int)(int8_t)(x >> (8 * f))); }
+// |v| of the four offset-binary bytes of a word
+__device__ __forceinline__ uint32_t abs4(uint32_t x) { return __vabsdiffu4(x, 0x80808080u); }
+__device__ __forceinline__ int byte_of(uint32_t x, int f) { return (int)__byte_perm(x, 0, 0x4440 + f); }
 
-// One word (4 frames) of a degree-D check: x[0..D) in, c->v words out (in place).
+// sign word of output j: XOR of the signs of all OTHER inputs.  Sx = XOR of the D offset-binary words
+// (bit 7 set = non-negative), so bit 7 of Sx ^ x_j is parity(D-1) ^ XOR_{i != j} neg_i.
+template <int DPARITY>
+__device__ __forceinline__ uint32_t sign_excluding(uint32_t Sx, uint32_t xj) {
+    return (DPARITY & 1) ? (~(Sx ^ xj) & 0x80808080u) : ((Sx ^ xj) & 0x80808080u);   // D-1 odd <=> D even
+}
+__device__ __forceinline__ uint32_t sign_excluding_rt(uint32_t Sx, uint32_t xj, int d) {
+    uint32_t s = (Sx ^ xj) & 0x80808080u;
+    return (d & 1) ? s : s ^ 0x80808080u;
+}
+
+// One word (4 frames) of a degree-D check: x[0..D) in (offset binary), c->v words out (in place).
 // Frame slots whose bit is set in `skip` (every lane's frame there has stopped) are not computed.
-template <int D, bool AMIN, bool HLIM>
-__device__ __forceinline__ void check_word(uint32_t (&x)[D], uint32_t skip, const Tables& tb) {
-    uint32_t S = 0;
+// SKIP = false is the steady-state path: no per-frame branches, so the four frames of the word form
+// one basic block and their fold chains interleave (the chains are latency-bound: IMAD -> LDS -> VIADDMNMX).
+template <int D, bool AMIN, bool HLIM, bool SKIP>
+__device__ __forceinline__ void check_word(uint32_t (&x)[D], uint32_t skip, const Tables& tb, const Consts& k) {
+    uint32_t S = 0, A[D], om[D];
 #pragma unroll
-    for (int j = 0; j < D; ++j) S ^= x[j];
-    uint32_t om[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) om[j] = 0;
+    for (int j = 0; j < D; ++j) { S ^= x[j]; A[j] = abs4(x[j]); om[j] = 0; }
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
-        if (skip >> f & 1) continue;
+        if (SKIP && (skip >> f & 1)) continue;
         int a[D], r[D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) a[j] = mag_of(x[j], f);
+        for (int j = 0; j < D; ++j) a[j] = byte_of(A[j], f);
         if (AMIN) {
             int amin = a[0], arg = 0;                // first minimum (min_by_key)
 #pragma unroll
@@ -131,8 +175,8 @@ __device__ __forceinline__ void check_word(uint32_t (&x)[D], uint32_t skip, cons
             int delta = -1;
 #pragma unroll
             for (int j = 0; j < D; ++j)
-                if (j != arg) delta = delta < 0 ? a[j] : hop(a[j], delta, tb);
-            int d2 = hop(delta, amin, tb);
+                if (j != arg) delta = delta < 0 ? a[j] : hop(a[j], delta, tb, k);
+            int d2 = hop(delta, amin, tb, k);
 #pragma unroll
             for (int j = 0; j < D; ++j) r[j] = j == arg ? delta : d2;
         } else if (D == 2) {
@@ -141,40 +185,52 @@ __device__ __forceinline__ void check_word(uint32_t (&x)[D], uint32_t skip, cons
         } else {
             int acc = a[1];
 #pragma unroll
-            for (int i = 2; i < D; ++i) acc = gop(a[i], acc, tb);
+            for (int i = 2; i < D; ++i) acc = gop(a[i], acc, tb, k);
             r[0] = acc;
             int P = a[0];                            // fold(x_0 .. x_{j-1})
 #pragma unroll
             for (int j = 1; j < D; ++j) {
                 acc = P;
 #pragma unroll
-                for (int i = j + 1; i < D; ++i) acc = gop(a[i], acc, tb);
+                for (int i = j + 1; i < D; ++i) acc = gop(a[i], acc, tb, k);
                 r[j] = acc;
-                if (j < D - 1) P = gop(a[j], P, tb);
+                if (j < D - 1) P = gop(a[j], P, tb, k);
             }
         }
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             int mg = HLIM ? hardlimit(r[j]) : r[j];
-            om[j] |= (uint32_t)mg << (8 * f);
+            om[j] = f == 0 ? (uint32_t)mg : (uint32_t)imad(mg, k.sh[f], (int)om[j]);     // om |= mg << 8f on the FMA pipe
         }
     }
 #pragma unroll
-    for (int j = 0; j < D; ++j) x[j] = apply_signs(om[j], (S ^ x[j]) & 0x80808080u);
+    for (int j = 0; j < D; ++j) x[j] = apply_signs(om[j], sign_excluding<D - 1>(S, x[j]), k);
 }
 
 template <int NW, int MAXD, int D, bool AMIN, bool HLIM>
 __device__ __forceinline__ void check_fixed(Lane<NW> (&x)[MAXD], uint32_t* __restrict__ msg, size_t e0, int lane,
-                                            uint32_t skip, const Tables& tb) {
+                                            uint32_t skip, const Tables& tb, const Consts& k) {
+    if (skip == 0) {
 #pragma unroll
-    for (int q = 0; q < NW; ++q) {
-        if (((skip >> (4 * q)) & 0xfu) == 0xfu) continue;
-        uint32_t xw[D];
+        for (int q = 0; q < NW; ++q) {
+            uint32_t xw[D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) xw[j] = x[j].w[q];
-        check_word<D, AMIN, HLIM>(xw, skip >> (4 * q), tb);
+            for (int j = 0; j < D; ++j) xw[j] = x[j].w[q];
+            check_word<D, AMIN, HLIM, false>(xw, 0, tb, k);
 #pragma unroll
-        for (int j = 0; j < D; ++j) x[j].w[q] = xw[j];
+            for (int j = 0; j < D; ++j) x[j].w[q] = xw[j];
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            if (((skip >> (4 * q)) & 0xfu) == 0xfu) continue;
+            uint32_t xw[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) xw[j] = x[j].w[q];
+            check_word<D, AMIN, HLIM, true>(xw, skip >> (4 * q), tb, k);
+#pragma unroll
+            for (int j = 0; j < D; ++j) x[j].w[q] = xw[j];
+        }
     }
 #pragma unroll
     for (int j = 0; j < D; ++j) st_lane<NW>(msg, e0 + j, lane, x[j]);
@@ -182,27 +238,28 @@ __device__ __forceinline__ void check_fixed(Lane<NW> (&x)[MAXD], uint32_t* __res
 
 // any degree up to kMaxGenericD; one word at a time, inputs staged in local memory
 template <int NW, bool AMIN, bool HLIM>
-__device__ __noinline__ void check_generic(uint32_t* __restrict__ msg, size_t e0, int d, int lane, uint32_t skip, const Tables& tb) {
+__device__ __noinline__ void check_generic(uint32_t* __restrict__ msg, size_t e0, int d, int lane, uint32_t skip, const Tables& tb,
+                                           const Consts& k) {
     for (int q = 0; q < NW; ++q) {
-        uint32_t x[kMaxGenericD], om[kMaxGenericD];
+        uint32_t x[kMaxGenericD], A[kMaxGenericD], om[kMaxGenericD];
         uint32_t S = 0;
         uint32_t* mrow = msg + (e0 * kLanes + lane) * NW + q;
-        for (int j = 0; j < d; ++j) { x[j] = __ldcg(mrow + (size_t)j * kLanes * NW); S ^= x[j]; om[j] = 0; }
+        for (int j = 0; j < d; ++j) { x[j] = __ldcg(mrow + (size_t)j * kLanes * NW); S ^= x[j]; A[j] = abs4(x[j]); om[j] = 0; }
         for (int f = 0; f < 4; ++f) {
             if (skip >> (4 * q + f) & 1) continue;
             if (AMIN) {
                 int amin = 1 << 20, arg = 0;
                 for (int j = 0; j < d; ++j) {
-                    int a = mag_of(x[j], f);
+                    int a = (int)((A[j] >> (8 * f)) & 0xffu);
                     if (a < amin) { amin = a; arg = j; }
                 }
                 int delta = -1;
                 for (int j = 0; j < d; ++j) {
                     if (j == arg) continue;
-                    int a = mag_of(x[j], f);
-                    delta = delta < 0 ? a : hop(a, delta, tb);
+                    int a = (int)((A[j] >> (8 * f)) & 0xffu);
+                    delta = delta < 0 ? a : hop(a, delta, tb, k);
                 }
-                int d2 = hop(delta, amin, tb);
+                int d2 = hop(delta, amin, tb, k);
                 if (HLIM) { delta = hardlimit(delta); d2 = hardlimit(d2); }
                 for (int j = 0; j < d; ++j) om[j] |= (uint32_t)(j == arg ? delta : d2) << (8 * f);
             } else {
@@ -211,29 +268,26 @@ __device__ __noinline__ void check_generic(uint32_t* __restrict__ msg, size_t e0
                     int acc = -1;
                     if (j > 0) acc = P;
                     for (int i = j + 1; i < d; ++i) {
-                        int a = mag_of(x[i], f);
-                        acc = acc < 0 ? a : gop(a, acc, tb);
+                        int a = (int)((A[i] >> (8 * f)) & 0xffu);
+                        acc = acc < 0 ? a : gop(a, acc, tb, k);
                     }
                     int mg = HLIM ? hardlimit(acc) : acc;
                     om[j] |= (uint32_t)mg << (8 * f);
-                    int aj = mag_of(x[j], f);
-                    P = j == 0 ? aj : gop(aj, P, tb);
+                    int aj = (int)((A[j] >> (8 * f)) & 0xffu);
+                    P = j == 0 ? aj : gop(aj, P, tb, k);
                 }
             }
         }
-        for (int j = 0; j < d; ++j) __stcg(mrow + (size_t)j * kLanes * NW, apply_signs(om[j], (S ^ x[j]) & 0x80808080u));
+        for (int j = 0; j < d; ++j) __stcg(mrow + (size_t)j * kLanes * NW, apply_signs(om[j], sign_excluding_rt(S, x[j], d), k));
     }
 }
 
 // ---- variable node, arithmetic.rs:622-654, on 2 x (2 frames as s16x2) per word -----------------
-// Everything is kept in a biased unsigned domain (value + 128 per term) so that plain 32-bit adds
-// never carry between the two 16-bit halves; the bias is removed inside the DPX add-min op.
+// Offset-binary bytes (value + 128) widen to unsigned 16-bit halves, so plain 32-bit adds never carry
+// between the two halves; the bias is removed inside the DPX add-min op.
 struct VarAcc { uint32_t lo, hi; };
 
-__device__ __forceinline__ VarAcc widen_biased(uint32_t w_i8x4) {
-    uint32_t b = w_i8x4 ^ 0x80808080u;              // int8 + 128, per byte
-    return {prmt(b, 0, 0x4140), prmt(b, 0, 0x4342)};
-}
+__device__ __forceinline__ VarAcc widen(uint32_t w_ob) { return {prmt(w_ob, 0, 0x4140), prmt(w_ob, 0, 0x4342)}; }
 
 __device__ __forceinline__ uint32_t rep16(int v) { return ((uint32_t)v & 0xffffu) * 0x00010001u; }
 
@@ -243,7 +297,8 @@ __device__ __forceinline__ uint32_t clip127(uint32_t v) {      // per-half clamp
 
 struct VarConsts { uint32_t negL, negK; bool jones; };
 __device__ __forceinline__ VarConsts var_consts(int d, bool jones) {
-    return {rep16(-128 * (d + 1)), jones ? rep16(-256) : rep16(-128 * d), jones};
+    // negK also re-adds the +128 of the offset-binary output
+    return {rep16(-128 * (d + 1)), jones ? rep16(-256 + 128) : rep16(-128 * d + 128), jones};
 }
 
 // One word of a variable node once its biased sum (input + all check messages) is known: returns
@@ -264,20 +319,23 @@ __device__ __forceinline__ uint32_t var_posterior(VarAcc sum, const VarConsts& k
     return pack_bits4((prmt(zlo, zhi, 0x7531) >> 7) & 0x01010101u);
 }
 
-// clip(L - c_j) = clamp((base - c'_j) - K, -127, 127); base >= c'_j in both halves
-__device__ __forceinline__ uint32_t var_message(uint32_t c_i8x4, uint32_t base_lo, uint32_t base_hi, uint32_t negK) {
-    VarAcc c = widen_biased(c_i8x4);
-    uint32_t vlo = __vmaxs2(__viaddmin_s16x2(base_lo - c.lo, negK, 0x007f007fu), 0xff81ff81u);
-    uint32_t vhi = __vmaxs2(__viaddmin_s16x2(base_hi - c.hi, negK, 0x007f007fu), 0xff81ff81u);
+// offset-binary clip(L - c_j) + 128 = clamp((base - c'_j) - K + 128, 1, 255); base >= c'_j in both halves
+__device__ __forceinline__ uint32_t var_message(uint32_t c_ob, uint32_t base_lo, uint32_t base_hi, uint32_t negK, const Consts& k) {
+    VarAcc c = widen(c_ob);
+    uint32_t ulo = (uint32_t)imad((int)c.lo, k.m1, (int)base_lo), uhi = (uint32_t)imad((int)c.hi, k.m1, (int)base_hi);
+    uint32_t vlo = __vmaxs2(__viaddmin_s16x2(ulo, negK, 0x00ff00ffu), 0x00010001u);
+    uint32_t vhi = __vmaxs2(__viaddmin_s16x2(uhi, negK, 0x00ff00ffu), 0x00010001u);
     return prmt(vlo, vhi, 0x6420);
 }
 
-// U variables of degree D per warp iteration: all index loads, then all message loads, then math
+// U variables of degree D per warp iteration: all index loads, then all message loads, then math.
+// (A shared-memory cp.async pipeline like the check pass's was measured slower here: 45.5 vs 35 ms per
+// iteration of the bench workload — the gather is latency-bound per line, not issue-bound.)
 template <int NW, int D, int U>
 __device__ __forceinline__ void var_class(uint32_t* __restrict__ msg, typename HBitsT<NW>::type* __restrict__ hbit,
                                           const uint32_t* __restrict__ inq, const int* __restrict__ vlist,
                                           const int* __restrict__ vedges, int count, bool jones, bool deg1clip,
-                                          uint32_t skip, int warp, int lane) {
+                                          uint32_t skip, int warp, int lane, const Consts& kc) {
     const VarConsts k = var_consts(D, jones);
     for (int i = warp * U; i < count; i += kWarps * U) {
         int e[U][D];
@@ -302,22 +360,22 @@ __device__ __forceinline__ void var_class(uint32_t* __restrict__ msg, typename H
             uint32_t hb = 0;
 #pragma unroll
             for (int q = 0; q < NW; ++q) {
-                if (((skip >> (4 * q)) & 0xfu) == 0xfu) continue;
-                VarAcc sum = widen_biased(inw[u].w[q]);
+                if (skip != 0 && ((skip >> (4 * q)) & 0xfu) == 0xfu) continue;
+                VarAcc sum = widen(inw[u].w[q]);
                 if (D == 1 && deg1clip) {             // arithmetic.rs:826-842, biased: [12, 244]
                     sum.lo = __vmaxu2(__vminu2(sum.lo, rep16(244)), rep16(12));
                     sum.hi = __vmaxu2(__vminu2(sum.hi, rep16(244)), rep16(12));
                 }
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
-                    VarAcc c = widen_biased(w[u][j].w[q]);
-                    sum.lo += c.lo;
-                    sum.hi += c.hi;
+                    VarAcc c = widen(w[u][j].w[q]);
+                    sum.lo = (uint32_t)imad((int)c.lo, kc.one, (int)sum.lo);
+                    sum.hi = (uint32_t)imad((int)c.hi, kc.one, (int)sum.hi);
                 }
                 uint32_t blo, bhi;
                 hb |= var_posterior(sum, k, blo, bhi) << (4 * q);
 #pragma unroll
-                for (int j = 0; j < D; ++j) w[u][j].w[q] = var_message(w[u][j].w[q], blo, bhi, k.negK);
+                for (int j = 0; j < D; ++j) w[u][j].w[q] = var_message(w[u][j].w[q], blo, bhi, k.negK, kc);
             }
 #pragma unroll
             for (int j = 0; j < D; ++j) {
@@ -332,7 +390,8 @@ __device__ __forceinline__ void var_class(uint32_t* __restrict__ msg, typename H
 template <int NW>
 __device__ __noinline__ void var_generic_class(uint32_t* __restrict__ msg, typename HBitsT<NW>::type* __restrict__ hbit,
                                                const uint32_t* __restrict__ inq, const DeviceGraph& g,
-                                               const int* __restrict__ vlist, int count, bool jones, int warp, int lane) {
+                                               const int* __restrict__ vlist, int count, bool jones, int warp, int lane,
+                                               const Consts& kc) {
     for (int i = warp; i < count; i += kWarps) {
         int v = __ldg(vlist + i);
         int p0 = __ldg(g.col_ptr + v), d = __ldg(g.col_ptr + v + 1) - p0;
@@ -340,9 +399,9 @@ __device__ __noinline__ void var_generic_class(uint32_t* __restrict__ msg, typen
         const VarConsts k = var_consts(d, jones);
         uint32_t hb = 0;
         for (int q = 0; q < NW; ++q) {
-            VarAcc sum = widen_biased(__ldg(inq + ((size_t)v * kLanes + lane) * NW + q));
+            VarAcc sum = widen(__ldg(inq + ((size_t)v * kLanes + lane) * NW + q));
             for (int j = 0; j < d; ++j) {
-                VarAcc c = widen_biased(__ldcg(msg + ((size_t)__ldg(ce + j) * kLanes + lane) * NW + q));
+                VarAcc c = widen(__ldcg(msg + ((size_t)__ldg(ce + j) * kLanes + lane) * NW + q));
                 sum.lo += c.lo;
                 sum.hi += c.hi;
             }
@@ -350,7 +409,7 @@ __device__ __noinline__ void var_generic_class(uint32_t* __restrict__ msg, typen
             hb |= var_posterior(sum, k, blo, bhi) << (4 * q);
             for (int j = 0; j < d; ++j) {
                 uint32_t* pm = msg + ((size_t)__ldg(ce + j) * kLanes + lane) * NW + q;
-                __stcg(pm, var_message(__ldcg(pm), blo, bhi, k.negK));
+                __stcg(pm, var_message(__ldcg(pm), blo, bhi, k.negK, kc));
             }
         }
         for (int j = 0; j < d; ++j) hbit[(size_t)__ldg(ce + j) * kLanes + lane] = (typename HBitsT<NW>::type)hb;
@@ -358,11 +417,14 @@ __device__ __noinline__ void var_generic_class(uint32_t* __restrict__ msg, typen
 }
 
 template <int NW, bool AMIN, bool HLIM>
-__global__ void __launch_bounds__(kWarps * 32) flood_i8_kernel(FloodI8Params p) {
+__global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kernel(FloodI8Params p) {
     using HB = typename HBitsT<NW>::type;
     constexpr int MAXD = NW == 1 ? 10 : 8;          // check degrees with an unrolled register path
     constexpr uint32_t kAll = NW == 1 ? 0xfu : 0xffffu;
     constexpr int kFrames = kTileFrames * NW;
+    constexpr int kMsgBytes = MAXD * kLanes * NW * 4;                 // one check's message lines
+    constexpr int kStageBytes = kMsgBytes + MAXD * kLanes * (int)sizeof(HB);
+    extern __shared__ __align__(16) uint8_t dsm[];                    // [kWarps][2][kStageBytes]
     __shared__ __align__(128) Tables tb;
     __shared__ uint32_t s_unsat[kLanes];
     __shared__ uint32_t s_done[kLanes];
@@ -371,6 +433,7 @@ __global__ void __launch_bounds__(kWarps * 32) flood_i8_kernel(FloodI8Params p) 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t tile = blockIdx.x;
     const DeviceGraph& g = p.g;
+    const Consts kc = {p.c_m1, p.c_one, p.c_m2, p.c_ff, {1, p.c_sh8, p.c_sh16, p.c_sh24}};
     uint32_t* msg = p.msg + tile * (size_t)g.E * kLanes * NW;
     HB* hbit = static_cast<HB*>(p.hbit) + tile * (size_t)g.E * kLanes;
     const uint32_t* inq = p.inq + tile * (size_t)g.n * kLanes * NW;
@@ -387,16 +450,19 @@ __global__ void __launch_bounds__(kWarps * 32) flood_i8_kernel(FloodI8Params p) 
     if (threadIdx.x == 0) s_skip = 0;
 
     // flooding.rs:88-100: first variable messages are the quantised channel LLRs; the
-    // "iteration 0" hard decisions are the raw LLR signs (flooding.rs:57)
-    for (int v = warp; v < g.n; v += kWarps) {
-        Lane<NW> w = ld_lane<NW>(inq, (size_t)v, lane);
-        HB hb = raw0[(size_t)v * kLanes + lane];
-        int p0 = __ldg(g.col_ptr + v), p1 = __ldg(g.col_ptr + v + 1);
-        for (int q = p0; q < p1; ++q) {
-            size_t e = (size_t)__ldg(g.col_edge + q);
-            st_lane<NW>(msg, e, lane, w);
-            hbit[e * kLanes + lane] = hb;
-        }
+    // "iteration 0" hard decisions are the raw LLR signs (flooding.rs:57).  Edge-parallel, four
+    // independent edges in flight per warp.
+    for (int e0 = warp * 4; e0 < g.E; e0 += kWarps * 4) {
+        int v[4];
+        Lane<NW> w[4];
+        HB hb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(g.col_idx + min(e0 + u, g.E - 1));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { w[u] = ld_lane<NW>(inq, (size_t)v[u], lane); hb[u] = raw0[(size_t)v[u] * kLanes + lane]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (e0 + u < g.E) { st_lane<NW>(msg, (size_t)(e0 + u), lane, w[u]); hbit[(size_t)(e0 + u) * kLanes + lane] = hb[u]; }
     }
     __syncthreads();
 
@@ -405,50 +471,64 @@ __global__ void __launch_bounds__(kWarps * 32) flood_i8_kernel(FloodI8Params p) 
         const uint32_t skip = s_skip;                // frame slots in which every lane has stopped
         uint32_t synd = 0;
         {
-            // software pipeline over this warp's checks: the loads of check c+kWarps are in flight
-            // while check c is being computed
-            Lane<NW> xn[MAXD] = {};
-            uint32_t hn[MAXD] = {};
-            int e0n = 0, dn = 0;
-            auto prefetch = [&](int c) {
-                e0n = __ldg(g.row_ptr + c);
-                dn = __ldg(g.row_ptr + c + 1) - e0n;
-#pragma unroll
-                for (int j = 0; j < MAXD; ++j) {
-                    hn[j] = 0;
-                    if (j < dn && dn <= MAXD) {
-                        hn[j] = hbit[(size_t)(e0n + j) * kLanes + lane];
-                        if (!last) xn[j] = ld_lane<NW>(msg, (size_t)(e0n + j), lane);
+            // Per-warp double buffer in shared memory, filled with 16-byte asynchronous copies: the
+            // messages and hard bits of check c+kWarps stream in while check c is being computed, at no
+            // register cost.  A check's D message lines (and its D hard-bit lines) are contiguous in HBM.
+            uint8_t* wbuf = dsm + (size_t)warp * 2 * kStageBytes;
+            auto prefetch = [&](int c, int stage, int& e0o, int& dout) {
+                const int e0 = __ldg(g.row_ptr + c), d = __ldg(g.row_ptr + c + 1) - e0;
+                e0o = e0; dout = d;
+                if (d <= MAXD) {
+                    uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
+                    if (!last) {
+                        const uint8_t* gm = reinterpret_cast<const uint8_t*>(msg + (size_t)e0 * kLanes * NW);
+                        for (int i = lane; i < d * 8 * NW; i += 32) cp_async16(sb + i * 16, gm + (size_t)i * 16);
                     }
+                    const uint8_t* gh = reinterpret_cast<const uint8_t*>(hbit + (size_t)e0 * kLanes);
+                    const int hchunks = d * (int)sizeof(HB) * 2;                     // 32 lanes * sizeof(HB) / 16
+                    if (lane < hchunks) cp_async16(sb + kMsgBytes + lane * 16, gh + (size_t)lane * 16);
                 }
+                cp_async_commit();
             };
-            int c = warp;
-            if (c < g.m) prefetch(c);
-            for (; c < g.m; c += kWarps) {
-                Lane<NW> x[MAXD];
-                uint32_t hb = 0;
+            int c = warp, stage = 0, e0n = 0, dn = 0;
+            if (c < g.m) prefetch(c, 0, e0n, dn);
+            for (; c < g.m; c += kWarps, stage ^= 1) {
                 const int e0 = e0n, d = dn;
-#pragma unroll
-                for (int j = 0; j < MAXD; ++j) { x[j] = xn[j]; hb ^= hn[j]; }
-                if (c + kWarps < g.m) prefetch(c + kWarps);
+                if (c + kWarps < g.m) { prefetch(c + kWarps, stage ^ 1, e0n, dn); cp_async_wait<1>(); }
+                else cp_async_wait<0>();
+                __syncwarp();
+                const uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
+                uint32_t hb = 0;
                 if (d > MAXD) {
                     for (int j = 0; j < d; ++j) hb ^= hbit[(size_t)(e0 + j) * kLanes + lane];
-                    if (!last) check_generic<NW, AMIN, HLIM>(msg, (size_t)e0, d, lane, skip, tb);
-                } else if (!last) {
-                    switch (d) {
-                        case 2: check_fixed<NW, MAXD, 2, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
-                        case 3: check_fixed<NW, MAXD, 3, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
-                        case 4: check_fixed<NW, MAXD, 4, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
-                        case 5: check_fixed<NW, MAXD, 5, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
-                        case 6: check_fixed<NW, MAXD, 6, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
-                        case 7: check_fixed<NW, MAXD, 7, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
-                        case 8: check_fixed<NW, MAXD, 8, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
-                        case 9: if (MAXD >= 9) check_fixed<NW, MAXD, (MAXD >= 9 ? 9 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
-                        case 10: if (MAXD >= 10) check_fixed<NW, MAXD, (MAXD >= 10 ? 10 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb); break;
-                        default: break;   // degree 0; degree 1 is refused before launch (reference panics)
+                    if (!last) check_generic<NW, AMIN, HLIM>(msg, (size_t)e0, d, lane, skip, tb, kc);
+                } else {
+                    const HB* sh = reinterpret_cast<const HB*>(sb + kMsgBytes);
+#pragma unroll
+                    for (int j = 0; j < MAXD; ++j)
+                        if (j < d) hb ^= sh[j * kLanes + lane];
+                    if (!last) {
+                        Lane<NW> x[MAXD];
+                        const Lane<NW>* sx = reinterpret_cast<const Lane<NW>*>(sb);
+#pragma unroll
+                        for (int j = 0; j < MAXD; ++j)
+                            if (j < d) x[j] = sx[j * kLanes + lane];
+                        switch (d) {
+                            case 2: check_fixed<NW, MAXD, 2, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
+                            case 3: check_fixed<NW, MAXD, 3, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
+                            case 4: check_fixed<NW, MAXD, 4, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
+                            case 5: check_fixed<NW, MAXD, 5, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
+                            case 6: check_fixed<NW, MAXD, 6, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
+                            case 7: check_fixed<NW, MAXD, 7, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
+                            case 8: check_fixed<NW, MAXD, 8, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
+                            case 9: if (MAXD >= 9) check_fixed<NW, MAXD, (MAXD >= 9 ? 9 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
+                            case 10: if (MAXD >= 10) check_fixed<NW, MAXD, (MAXD >= 10 ? 10 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
+                            default: break;   // degree 0; degree 1 is refused before launch (reference panics)
+                        }
                     }
                 }
                 synd |= hb;
+                __syncwarp();          // every lane is done with this stage before it is refilled
             }
         }
         if (synd) atomicOr(&s_unsat[lane], synd);
@@ -474,7 +554,7 @@ __global__ void __launch_bounds__(kWarps * 32) flood_i8_kernel(FloodI8Params p) 
                         for (int q = 0; q < NW; ++q) {
                             uint32_t qw = __ldg(inq + o * NW + q);
 #pragma unroll
-                            for (int b = 0; b < 4; ++b) hb |= (uint32_t)((int8_t)(qw >> (8 * b)) <= 0) << (4 * q + b);
+                            for (int b = 0; b < 4; ++b) hb |= (uint32_t)(((qw >> (8 * b)) & 0xffu) <= 128u) << (4 * q + b);
                         }
                     }
                     fin[o] = (HB)((fin[o] & ~stop) | (hb & stop));
@@ -497,32 +577,41 @@ __global__ void __launch_bounds__(kWarps * 32) flood_i8_kernel(FloodI8Params p) 
             const int deg = p.vc.deg[k], off = p.vc.off[k], cnt = p.vc.off[k + 1] - off;
             const int* vl = p.vc.var_list + off;
             const int* ve = p.vc.var_edges + p.vc.edge_off[k];
+#define LDPC_VAR_CASE(D_, U_)                                                                                          \
+    case D_: var_class<NW, D_, U_>(msg, hbit, inq, vl, ve, cnt, jones, D_ == 1 && d1c, vskip, warp, lane, kc); break;
             constexpr int U3 = NW == 1 ? 4 : 2, U8 = NW == 1 ? 2 : 1;
             switch (deg) {
-                case 1: var_class<NW, 1, U3>(msg, hbit, inq, vl, ve, cnt, jones, d1c, vskip, warp, lane); break;
-                case 2: var_class<NW, 2, U3>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
-                case 3: var_class<NW, 3, U3>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
-                case 4: var_class<NW, 4, U8>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
-                case 5: var_class<NW, 5, U8>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
-                case 6: var_class<NW, 6, U8>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
-                case 7: var_class<NW, 7, U8>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
-                case 8: var_class<NW, 8, U8>(msg, hbit, inq, vl, ve, cnt, jones, false, vskip, warp, lane); break;
-                default: var_generic_class<NW>(msg, hbit, inq, g, vl, cnt, jones, warp, lane); break;
+                LDPC_VAR_CASE(1, U3) LDPC_VAR_CASE(2, U3) LDPC_VAR_CASE(3, U3) LDPC_VAR_CASE(4, U8)
+                LDPC_VAR_CASE(5, U8) LDPC_VAR_CASE(6, U8) LDPC_VAR_CASE(7, U8) LDPC_VAR_CASE(8, U8)
+                default: var_generic_class<NW>(msg, hbit, inq, g, vl, cnt, jones, warp, lane, kc); break;
             }
+#undef LDPC_VAR_CASE
         }
         __syncthreads();
     }
 }
 
+template <int NW, bool AMIN, bool HLIM>
+void launch_one(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t stream) {
+    constexpr int MAXD = NW == 1 ? 10 : 8;
+    constexpr size_t stage = (size_t)MAXD * kLanes * NW * 4 + (size_t)MAXD * kLanes * sizeof(typename HBitsT<NW>::type);
+    constexpr size_t smem = (size_t)kWarps * 2 * stage;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(flood_i8_kernel<NW, AMIN, HLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    flood_i8_kernel<NW, AMIN, HLIM><<<dim3((unsigned)L.num_tiles), dim3(kWarps * 32), smem, stream>>>(p);
+}
+
 template <int NW>
 void launch_nw(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t stream) {
-    dim3 grid((unsigned)L.num_tiles), block(kWarps * 32);
     if (L.aminstar) {
-        if (L.hardlimit) flood_i8_kernel<NW, true, true><<<grid, block, 0, stream>>>(p);
-        else flood_i8_kernel<NW, true, false><<<grid, block, 0, stream>>>(p);
+        if (L.hardlimit) launch_one<NW, true, true>(L, p, stream);
+        else launch_one<NW, true, false>(L, p, stream);
     } else {
-        if (L.hardlimit) flood_i8_kernel<NW, false, true><<<grid, block, 0, stream>>>(p);
-        else flood_i8_kernel<NW, false, false><<<grid, block, 0, stream>>>(p);
+        if (L.hardlimit) launch_one<NW, false, true>(L, p, stream);
+        else launch_one<NW, false, false>(L, p, stream);
     }
 }
 
@@ -533,6 +622,7 @@ bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream) {
     p.g = L.graph; p.vc = L.classes;
     p.msg = L.msg; p.hbit = L.hbit; p.inq = L.inq; p.raw0 = L.raw0; p.final_hard = L.final_hard; p.iters = L.iters;
     p.max_iter = L.max_iter; p.jones = L.jones; p.deg1clip = L.deg1clip;
+    p.c_m1 = -1; p.c_one = 1; p.c_m2 = -2; p.c_ff = 0xff; p.c_sh8 = 1 << 8; p.c_sh16 = 1 << 16; p.c_sh24 = 1 << 24;
     if (L.words_per_lane == 4) launch_nw<4>(L, p, stream);
     else launch_nw<1>(L, p, stream);
     LDPC_CUDA_CHECK(cudaGetLastError());

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_kernel(IngestLaunch 
         TIn x = TIn(1);                                  // padding frames: clean all-zero codeword
         if (frame < p.nframes) x = src >= 0 ? llrs[frame * p.llrs_len + (size_t)src] : TIn(0);
         s_raw[lane * ST + fr] = x <= TIn(0) ? 1 : 0;
-        if (MODE == 0) s_q[lane * ST + fr] = (uint8_t)(int8_t)quantize_i8(x);
+        if (MODE == 0) s_q[lane * ST + fr] = (uint8_t)(quantize_i8(x) + 128);      // offset binary (flood_i8.cu)
         if (MODE == 1) s_f[lane * (TF + 1) + fr] = (float)x;
         if (MODE == 2) s_d[lane * (TF + 1) + fr] = (double)x;
         if (MODE == 3) s_h[lane * (TF + 2) + fr] = (int16_t)quantize_i8(x);
