@@ -49,6 +49,9 @@ EXPORTED_SYMBOLS = tuple(_SIGS.keys())
 
 
 def library_path() -> str:
+    override = os.environ.get("LDPC_B200_LIB")     # experiment builds of the same CUDA library (tools/build_variant.py)
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libldpc_toolbox.so")
 
 

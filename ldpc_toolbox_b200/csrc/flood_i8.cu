@@ -68,6 +68,16 @@ struct Consts { int m1, one, m2, ff, sh[4]; };
 #define LDPC_I8_MINBLOCKS 2
 #endif
 constexpr int kWarps = LDPC_I8_WARPS;            // warps per CTA
+
+#ifdef LDPC_I8_PROFILE
+// experiment-only: SM-clock cycles thread 0 of every CTA spent in {init, check pass, stop logic, variable pass}, [4] = CTA-iterations
+__device__ unsigned long long g_i8_prof[8];
+#define PROF_T(var) long long var = clock64()
+#define PROF_ADD(slot, a, b) do { if (threadIdx.x == 0) atomicAdd(&g_i8_prof[slot], (unsigned long long)((b) - (a))); } while (0)
+#else
+#define PROF_T(var) do {} while (0)
+#define PROF_ADD(slot, a, b) do {} while (0)
+#endif
 constexpr int kMaxGenericD = 64;     // larger rows are rejected when the decoder is built
 
 template <int NW> struct Lane { uint32_t w[NW]; };
@@ -337,23 +347,36 @@ __device__ __forceinline__ void var_class(uint32_t* __restrict__ msg, typename H
                                           const int* __restrict__ vedges, int count, bool jones, bool deg1clip,
                                           uint32_t skip, int warp, int lane, const Consts& kc) {
     const VarConsts k = var_consts(D, jones);
-    for (int i = warp * U; i < count; i += kWarps * U) {
-        int e[U][D];
+    // indices of this warp's next group are fetched while the current group's lines are in flight
+    auto load_idx = [&](int i, int (&e)[U][D], int (&v)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            int ii = i + u < count ? i + u : i;
+            v[u] = __ldg(vlist + ii);
+#pragma unroll
+            for (int j = 0; j < D; ++j) e[u][j] = __ldg(vedges + (size_t)ii * D + j);
+        }
+    };
+    int i = warp * U;
+    if (i >= count) return;
+    int e[U][D], v[U];
+    load_idx(i, e, v);
+    for (; i < count; i += kWarps * U) {
         Lane<NW> w[U][D], inw[U];
         bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             ok[u] = i + u < count;
-            int ii = ok[u] ? i + u : i;
-            int v = __ldg(vlist + ii);
-#pragma unroll
-            for (int j = 0; j < D; ++j) e[u][j] = __ldg(vedges + (size_t)ii * D + j);
-            inw[u] = ld_lane<NW>(inq, (size_t)v, lane);
+            inw[u] = ld_lane<NW>(inq, (size_t)v[u], lane);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int j = 0; j < D; ++j) w[u][j] = ld_lane<NW>(msg, (size_t)e[u][j], lane);
+#ifdef LDPC_I8_VPREF
+        int en[U][D], vn[U];
+        if (i + kWarps * U < count) load_idx(i + kWarps * U, en, vn);
+#endif
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (!ok[u]) continue;
@@ -383,6 +406,16 @@ __device__ __forceinline__ void var_class(uint32_t* __restrict__ msg, typename H
                 hbit[(size_t)e[u][j] * kLanes + lane] = (typename HBitsT<NW>::type)hb;
             }
         }
+#ifdef LDPC_I8_VPREF
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            v[u] = vn[u];
+#pragma unroll
+            for (int j = 0; j < D; ++j) e[u][j] = en[u][j];
+        }
+#else
+        if (i + kWarps * U < count) load_idx(i + kWarps * U, e, v);
+#endif
     }
 }
 
@@ -448,6 +481,7 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
     if (threadIdx.x < 128) tb.Tp[threadIdx.x] = (int8_t)table_T(threadIdx.x);
     if (threadIdx.x < kLanes) { s_unsat[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
     if (threadIdx.x == 0) s_skip = 0;
+    PROF_T(pt_init0);
 
     // flooding.rs:88-100: first variable messages are the quantised channel LLRs; the
     // "iteration 0" hard decisions are the raw LLR signs (flooding.rs:57).  Edge-parallel, four
@@ -465,8 +499,11 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
             if (e0 + u < g.E) { st_lane<NW>(msg, (size_t)(e0 + u), lane, w[u]); hbit[(size_t)(e0 + u) * kLanes + lane] = hb[u]; }
     }
     __syncthreads();
+    PROF_T(pt_init1);
+    PROF_ADD(0, pt_init0, pt_init1);
 
     for (int it = 1;; ++it) {
+        PROF_T(pt_c0);
         const bool last = it > p.max_iter;           // only the syndrome of iteration max_iter is left
         const uint32_t skip = s_skip;                // frame slots in which every lane has stopped
         uint32_t synd = 0;
@@ -475,9 +512,13 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
             // messages and hard bits of check c+kWarps stream in while check c is being computed, at no
             // register cost.  A check's D message lines (and its D hard-bit lines) are contiguous in HBM.
             uint8_t* wbuf = dsm + (size_t)warp * 2 * kStageBytes;
-            auto prefetch = [&](int c, int stage, int& e0o, int& dout) {
-                const int e0 = __ldg(g.row_ptr + c), d = __ldg(g.row_ptr + c + 1) - e0;
-                e0o = e0; dout = d;
+            // row_ptr of the check after next is fetched one step early, so issuing a stage never waits on it
+            auto row_of = [&](int c, int& e0o, int& dout) {
+                const int cc = min(c, g.m - 1);
+                e0o = __ldg(g.row_ptr + cc);
+                dout = __ldg(g.row_ptr + cc + 1) - e0o;
+            };
+            auto issue = [&](int stage, int e0, int d) {
                 if (d <= MAXD) {
                     uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
                     if (!last) {
@@ -490,12 +531,20 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
                 }
                 cp_async_commit();
             };
-            int c = warp, stage = 0, e0n = 0, dn = 0;
-            if (c < g.m) prefetch(c, 0, e0n, dn);
+            int c = warp, stage = 0, e0c = 0, dc = 0, e0n = 0, dn = 0;
+            if (c < g.m) {
+                row_of(c, e0c, dc);
+                row_of(c + kWarps, e0n, dn);
+                issue(0, e0c, dc);
+            }
             for (; c < g.m; c += kWarps, stage ^= 1) {
-                const int e0 = e0n, d = dn;
-                if (c + kWarps < g.m) { prefetch(c + kWarps, stage ^ 1, e0n, dn); cp_async_wait<1>(); }
-                else cp_async_wait<0>();
+                const int e0 = e0c, d = dc;
+                e0c = e0n; dc = dn;
+                if (c + kWarps < g.m) {
+                    issue(stage ^ 1, e0c, dc);
+                    row_of(c + 2 * kWarps, e0n, dn);
+                    cp_async_wait<1>();
+                } else cp_async_wait<0>();
                 __syncwarp();
                 const uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
                 uint32_t hb = 0;
@@ -533,6 +582,8 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
         }
         if (synd) atomicOr(&s_unsat[lane], synd);
         __syncthreads();
+        PROF_T(pt_c1);
+        PROF_ADD(1, pt_c0, pt_c1);
         const uint32_t unsat = s_unsat[lane], done = s_done[lane];
         // frames whose hard decisions of iteration it-1 satisfy every check stop now
         // (flooding.rs:57-64 for it-1 == 0, :69-79 otherwise)
@@ -570,6 +621,8 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
         }
         const int all = __syncthreads_and(((done | stop) & kAll) == kAll);
         if (all || last) break;
+        PROF_T(pt_v0);
+        PROF_ADD(2, pt_c1, pt_v0);
 
         const bool jones = p.jones != 0, d1c = p.deg1clip != 0;
         const uint32_t vskip = s_skip;
@@ -579,7 +632,13 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
             const int* ve = p.vc.var_edges + p.vc.edge_off[k];
 #define LDPC_VAR_CASE(D_, U_)                                                                                          \
     case D_: var_class<NW, D_, U_>(msg, hbit, inq, vl, ve, cnt, jones, D_ == 1 && d1c, vskip, warp, lane, kc); break;
-            constexpr int U3 = NW == 1 ? 4 : 2, U8 = NW == 1 ? 2 : 1;
+            #ifndef LDPC_I8_U3
+#define LDPC_I8_U3 2
+#endif
+#ifndef LDPC_I8_U8
+#define LDPC_I8_U8 1
+#endif
+            constexpr int U3 = NW == 1 ? 4 : LDPC_I8_U3, U8 = NW == 1 ? 2 : LDPC_I8_U8;
             switch (deg) {
                 LDPC_VAR_CASE(1, U3) LDPC_VAR_CASE(2, U3) LDPC_VAR_CASE(3, U3) LDPC_VAR_CASE(4, U8)
                 LDPC_VAR_CASE(5, U8) LDPC_VAR_CASE(6, U8) LDPC_VAR_CASE(7, U8) LDPC_VAR_CASE(8, U8)
@@ -588,6 +647,9 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
 #undef LDPC_VAR_CASE
         }
         __syncthreads();
+        PROF_T(pt_v1);
+        PROF_ADD(3, pt_v0, pt_v1);
+        PROF_ADD(4, 0, 1);
     }
 }
 
@@ -606,6 +668,10 @@ void launch_one(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t str
 
 template <int NW>
 void launch_nw(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t stream) {
+#ifdef LDPC_I8_BENCH_ONLY      // experiment builds (tools/build_variant.py): only the north-star instantiation
+    if (NW == 4 && !L.aminstar && !L.hardlimit) launch_one<4, false, false>(L, p, stream);
+    return;
+#endif
     if (L.aminstar) {
         if (L.hardlimit) launch_one<NW, true, true>(L, p, stream);
         else launch_one<NW, true, false>(L, p, stream);
@@ -630,5 +696,15 @@ bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream) {
 }
 
 int flood_i8_max_row_degree() { return kMaxGenericD; }
+
+#ifdef LDPC_I8_PROFILE
+// experiment-only (not in include/ldpc_toolbox.h): read and reset the per-pass cycle counters
+extern "C" void ldpc_toolbox_debug_i8_profile(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_i8_prof, sizeof(unsigned long long) * 8);
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_i8_prof, z, sizeof(z));
+}
+#endif
 
 }  // namespace ldpc

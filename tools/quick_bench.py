@@ -53,8 +53,19 @@ for tiles in [int(t) for t in a.tiles.split(",")]:
             ms.append(e0.elapsed_time(e1))      # whole call (all chunks, ingest + BP + emit)
     ms = float(np.median(ms))
     fi = frames * a.iters / (ms * 1e-3)
+    prof = ""
+    try:
+        import ctypes
+        from ldpc_toolbox_b200 import capi
+        fn = capi.load().ldpc_toolbox_debug_i8_profile
+        buf = (ctypes.c_uint64 * 8)()
+        fn(buf)
+        tot = sum(buf[:4]) or 1
+        prof = " prof[init,check,stop,var]=" + ",".join(f"{buf[i] / tot:.3f}" for i in range(4)) + f" cyc/cta-iter={tot / max(buf[4], 1):.0f}"
+    except AttributeError:
+        pass
     print(f"{a.code} {a.impl} tiles={tiles} iters={a.iters} kernel_ms={ms:.2f} frame_iter/s={fi/1e6:.3f}M "
           f"alg_GB/s={fi*4*E/1e9:.0f} frac={fi*4*E/1e9/6553.6:.3f} conv={(its>=0).float().mean().item():.3f} "
-          f"its[min,max]={its.min().item()},{its.max().item()} stages={t}", flush=True)
+          f"its[min,max]={its.min().item()},{its.max().item()} stages={t}{prof}", flush=True)
     del dec, llrs
     torch.cuda.empty_cache()
