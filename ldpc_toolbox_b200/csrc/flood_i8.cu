@@ -35,6 +35,7 @@
 // the FMA pipe (IMAD) idles.  Plain adds/subtracts/shifts-and-ors on the critical path are therefore
 // written as mad.lo with a multiplier taken from a kernel parameter (ptxas cannot fold it), which
 // pins them to the FMA pipe: a fold step is IMAD + LDS + VIADDMNMX = one instruction per pipe.
+#include <cstdlib>
 #include <string>
 
 #include "decoder_impl.hpp"
@@ -57,7 +58,13 @@ struct FloodI8Params {
     int jones, deg1clip;
     // opaque multipliers for FMA-pipe integer arithmetic (see header): -1, 1, -2, 255, 2^8, 2^16, 2^24
     int c_m1, c_one, c_m2, c_ff, c_sh8, c_sh16, c_sh24;
+    long long dephase_ns;   // experiment: > 0 delays the second CTA of every SM by this long, -1: until the first CTA's first check pass is done
 };
+
+#ifdef LDPC_I8_DEPHASE
+__device__ unsigned g_sm_arrivals[512];
+__device__ unsigned g_sm_flag[512];
+#endif
 
 struct Consts { int m1, one, m2, ff, sh[4]; };
 
@@ -80,6 +87,7 @@ __device__ unsigned long long g_i8_prof[8];
 #endif
 constexpr int kMaxGenericD = 64;     // larger rows are rejected when the decoder is built
 
+__device__ __forceinline__ int lane_of_thread() { return threadIdx.x & 31; }
 template <int NW> struct Lane { uint32_t w[NW]; };
 template <int NW> struct HBitsT { using type = uint8_t; };
 template <> struct HBitsT<4> { using type = uint16_t; };
@@ -110,8 +118,33 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- TMA bulk copy global -> shared, completion on an mbarrier (one elected lane issues it) ------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 struct Tables {
     int8_t U[256];      // U[d + 127], d = a - acc in [-127, 127]
+    uint8_t V[256];     // V[d + 127] = d - U[d] = max(d, 0) + T[|d|]
     int8_t Tp[128];     // T[t]
 };
 
@@ -193,6 +226,7 @@ __device__ __forceinline__ void check_word(uint32_t (&x)[D], uint32_t skip, cons
             r[0] = a[1];
             r[1] = a[0];
         } else {
+#ifdef LDPC_I8_OLD_FOLD
             int acc = a[1];
 #pragma unroll
             for (int i = 2; i < D; ++i) acc = gop(a[i], acc, tb, k);
@@ -206,6 +240,41 @@ __device__ __forceinline__ void check_word(uint32_t (&x)[D], uint32_t skip, cons
                 r[j] = acc;
                 if (j < D - 1) P = gop(a[j], P, tb, k);
             }
+#else
+            // Difference form of the same folds: a chain is carried as idx = (next input) - acc, the
+            // table returns V[idx] = idx - U[idx], and the index of the following step is
+            //   a' - max(acc + U[idx], 0) = min(V[idx] + (a' - a), a')
+            // so a fold step is LDS + VIADDMNMX (the subtraction a' - a is shared by all chains), and a
+            // chain ends with acc = max(a - V[idx], 0).
+            int d1[D - 1];
+#pragma unroll
+            for (int i = 0; i + 1 < D; ++i) d1[i] = imad(a[i], k.m1, a[i + 1]);
+            // fold inputs a[i0..D) into a chain whose state is idx = a[i0] - acc
+            auto run = [&](int idx, int i0) {
+                int out = 0;
+#pragma unroll
+                for (int i = 2; i < D; ++i) {
+                    if (i < i0) continue;
+                    const int v = (int)tb.V[idx + 127];
+                    if (i + 1 < D) idx = __viaddmin_s32(v, d1[i], a[i + 1]);
+                    else out = __viaddmax_s32_relu(a[i], -v, 0);
+                }
+                return out;
+            };
+            r[0] = run(d1[1], 2);                                   // acc = a1, then a2 ..
+            r[1] = run(imad(a[0], k.m1, a[2]), 2);                  // acc = a0, then a2 ..
+            int dP = d1[0];                                         // a_{j-1} - P_{j-1}, P_1 = a0
+#pragma unroll
+            for (int j = 2; j < D; ++j) {                           // this lookup evaluates P_j = g(a_{j-1}, P_{j-1})
+                const int v = (int)tb.V[dP + 127];
+                if (j == D - 1) {
+                    r[j] = __viaddmax_s32_relu(a[j - 1], -v, 0);    // output D-1 is P_{D-1} itself
+                } else {
+                    dP = __viaddmin_s32(v, d1[j - 1], a[j]);        // a_j - P_j
+                    r[j] = run(imad(dP, k.one, d1[j]), j + 1);      // a_{j+1} - P_j, then a_{j+2} ..
+                }
+            }
+#endif
         }
 #pragma unroll
         for (int j = 0; j < D; ++j) {
@@ -462,6 +531,12 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
     __shared__ uint32_t s_unsat[kLanes];
     __shared__ uint32_t s_done[kLanes];
     __shared__ uint32_t s_skip;
+#ifdef LDPC_I8_TMA
+    __shared__ __align__(8) uint64_t s_bar[kWarps][2];     // one mbarrier per warp and stage
+    if (lane_of_thread() == 0) { mbar_init(&s_bar[threadIdx.x >> 5][0], 1); mbar_init(&s_bar[threadIdx.x >> 5][1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    uint32_t bar_phase = 0;                                 // bit s = parity the next wait on stage s uses
+#endif
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t tile = blockIdx.x;
@@ -477,11 +552,40 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
     for (int i = threadIdx.x; i < 255; i += blockDim.x) {
         int d = i - 127;
         tb.U[i] = (int8_t)(min(d, 0) - table_T(abs(d)));
+        tb.V[i] = (uint8_t)(max(d, 0) + table_T(abs(d)));
     }
     if (threadIdx.x < 128) tb.Tp[threadIdx.x] = (int8_t)table_T(threadIdx.x);
     if (threadIdx.x < kLanes) { s_unsat[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
     if (threadIdx.x == 0) s_skip = 0;
     PROF_T(pt_init0);
+#ifdef LDPC_I8_DEPHASE
+    __shared__ int s_slot, s_smid;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_smid = (int)smid;
+        s_slot = (int)(atomicAdd(&g_sm_arrivals[smid], 1u) & 1u);
+    }
+    __syncthreads();
+    if (p.dephase_ns != 0 && s_slot == 1) {
+        if (threadIdx.x == 0) {
+            if (p.dephase_ns > 0) {
+                unsigned long long t0, t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                do { __nanosleep(2000); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while ((long long)(t1 - t0) < p.dephase_ns);
+            } else {
+                unsigned long long t0, t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                do {                                  // bounded: never wait more than 40 ms for a partner
+                    __nanosleep(2000);
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                } while (atomicAdd(&g_sm_flag[s_smid], 0u) == 0u && (long long)(t1 - t0) < 40000000ll);
+                atomicExch(&g_sm_flag[s_smid], 0u);
+            }
+        }
+        __syncthreads();
+    }
+#endif
 
     // flooding.rs:88-100: first variable messages are the quantised channel LLRs; the
     // "iteration 0" hard decisions are the raw LLR signs (flooding.rs:57).  Edge-parallel, four
@@ -518,6 +622,17 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
                 e0o = __ldg(g.row_ptr + cc);
                 dout = __ldg(g.row_ptr + cc + 1) - e0o;
             };
+#ifdef LDPC_I8_TMA
+            auto issue = [&](int stage, int e0, int d) {
+                if (d <= MAXD && d > 0 && lane == 0) {
+                    uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
+                    const uint32_t mb = last ? 0u : (uint32_t)d * kLanes * NW * 4, hbytes = (uint32_t)d * kLanes * (uint32_t)sizeof(HB);
+                    mbar_expect_tx(&s_bar[warp][stage], mb + hbytes);
+                    if (!last) bulk_g2s(sb, msg + (size_t)e0 * kLanes * NW, mb, &s_bar[warp][stage]);
+                    bulk_g2s(sb + kMsgBytes, hbit + (size_t)e0 * kLanes, hbytes, &s_bar[warp][stage]);
+                }
+            };
+#else
             auto issue = [&](int stage, int e0, int d) {
                 if (d <= MAXD) {
                     uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
@@ -531,6 +646,7 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
                 }
                 cp_async_commit();
             };
+#endif
             int c = warp, stage = 0, e0c = 0, dc = 0, e0n = 0, dn = 0;
             if (c < g.m) {
                 row_of(c, e0c, dc);
@@ -540,12 +656,23 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
             for (; c < g.m; c += kWarps, stage ^= 1) {
                 const int e0 = e0c, d = dc;
                 e0c = e0n; dc = dn;
+#ifdef LDPC_I8_TMA
+                if (c + kWarps < g.m) {
+                    issue(stage ^ 1, e0c, dc);
+                    row_of(c + 2 * kWarps, e0n, dn);
+                }
+                if (d <= MAXD && d > 0) {
+                    mbar_wait(&s_bar[warp][stage], (bar_phase >> stage) & 1u);
+                    bar_phase ^= 1u << stage;
+                }
+#else
                 if (c + kWarps < g.m) {
                     issue(stage ^ 1, e0c, dc);
                     row_of(c + 2 * kWarps, e0n, dn);
                     cp_async_wait<1>();
                 } else cp_async_wait<0>();
                 __syncwarp();
+#endif
                 const uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
                 uint32_t hb = 0;
                 if (d > MAXD) {
@@ -584,6 +711,9 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
         __syncthreads();
         PROF_T(pt_c1);
         PROF_ADD(1, pt_c0, pt_c1);
+#ifdef LDPC_I8_DEPHASE
+        if (p.dephase_ns < 0 && it == 1 && s_slot == 0 && threadIdx.x == 0) atomicExch(&g_sm_flag[s_smid], 1u);
+#endif
         const uint32_t unsat = s_unsat[lane], done = s_done[lane];
         // frames whose hard decisions of iteration it-1 satisfy every check stop now
         // (flooding.rs:57-64 for it-1 == 0, :69-79 otherwise)
@@ -670,8 +800,7 @@ template <int NW>
 void launch_nw(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t stream) {
 #ifdef LDPC_I8_BENCH_ONLY      // experiment builds (tools/build_variant.py): only the north-star instantiation
     if (NW == 4 && !L.aminstar && !L.hardlimit) launch_one<4, false, false>(L, p, stream);
-    return;
-#endif
+#else
     if (L.aminstar) {
         if (L.hardlimit) launch_one<NW, true, true>(L, p, stream);
         else launch_one<NW, true, false>(L, p, stream);
@@ -679,6 +808,7 @@ void launch_nw(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t stre
         if (L.hardlimit) launch_one<NW, false, true>(L, p, stream);
         else launch_one<NW, false, false>(L, p, stream);
     }
+#endif
 }
 
 }  // namespace
@@ -688,6 +818,8 @@ bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream) {
     p.g = L.graph; p.vc = L.classes;
     p.msg = L.msg; p.hbit = L.hbit; p.inq = L.inq; p.raw0 = L.raw0; p.final_hard = L.final_hard; p.iters = L.iters;
     p.max_iter = L.max_iter; p.jones = L.jones; p.deg1clip = L.deg1clip;
+    p.dephase_ns = 0;
+    if (const char* e = getenv("LDPC_I8_DEPHASE_US")) p.dephase_ns = atoll(e) < 0 ? -1 : atoll(e) * 1000;
     p.c_m1 = -1; p.c_one = 1; p.c_m2 = -2; p.c_ff = 0xff; p.c_sh8 = 1 << 8; p.c_sh16 = 1 << 16; p.c_sh24 = 1 << 24;
     if (L.words_per_lane == 4) launch_nw<4>(L, p, stream);
     else launch_nw<1>(L, p, stream);

@@ -51,6 +51,7 @@ for tiles in [int(t) for t in a.tiles.split(",")]:
         t = dec.last_timing()
         if r:
             ms.append(e0.elapsed_time(e1))      # whole call (all chunks, ingest + BP + emit)
+    all_ms = ",".join(f"{m:.0f}" for m in ms)
     ms = float(np.median(ms))
     fi = frames * a.iters / (ms * 1e-3)
     prof = ""
@@ -66,6 +67,6 @@ for tiles in [int(t) for t in a.tiles.split(",")]:
         pass
     print(f"{a.code} {a.impl} tiles={tiles} iters={a.iters} kernel_ms={ms:.2f} frame_iter/s={fi/1e6:.3f}M "
           f"alg_GB/s={fi*4*E/1e9:.0f} frac={fi*4*E/1e9/6553.6:.3f} conv={(its>=0).float().mean().item():.3f} "
-          f"its[min,max]={its.min().item()},{its.max().item()} stages={t}{prof}", flush=True)
+          f"its[min,max]={its.min().item()},{its.max().item()} reps_ms=[{all_ms}] stages={t}{prof}", flush=True)
     del dec, llrs
     torch.cuda.empty_cache()
