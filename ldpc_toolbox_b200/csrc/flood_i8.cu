@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
     __shared__ uint32_t s_unsat[kLanes];
     __shared__ uint32_t s_done[kLanes];
     __shared__ uint32_t s_skip;
-#ifdef LDPC_I8_TMA
+#ifndef LDPC_I8_NO_TMA
     __shared__ __align__(8) uint64_t s_bar[kWarps][2];     // one mbarrier per warp and stage
     if (lane_of_thread() == 0) { mbar_init(&s_bar[threadIdx.x >> 5][0], 1); mbar_init(&s_bar[threadIdx.x >> 5][1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -612,9 +612,11 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
         const uint32_t skip = s_skip;                // frame slots in which every lane has stopped
         uint32_t synd = 0;
         {
-            // Per-warp double buffer in shared memory, filled with 16-byte asynchronous copies: the
-            // messages and hard bits of check c+kWarps stream in while check c is being computed, at no
-            // register cost.  A check's D message lines (and its D hard-bit lines) are contiguous in HBM.
+            // Per-warp double buffer in shared memory: the messages and hard bits of check c+kWarps stream
+            // in while check c is being computed, at no register cost.  A check's D message lines (and its
+            // D hard-bit lines) are contiguous in HBM, so one elected lane moves each with a single TMA bulk
+            // copy (cp.async.bulk) that completes on the stage's mbarrier; -DLDPC_I8_NO_TMA keeps the older
+            // per-lane 16-byte cp.async path for comparison.
             uint8_t* wbuf = dsm + (size_t)warp * 2 * kStageBytes;
             // row_ptr of the check after next is fetched one step early, so issuing a stage never waits on it
             auto row_of = [&](int c, int& e0o, int& dout) {
@@ -622,7 +624,7 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
                 e0o = __ldg(g.row_ptr + cc);
                 dout = __ldg(g.row_ptr + cc + 1) - e0o;
             };
-#ifdef LDPC_I8_TMA
+#ifndef LDPC_I8_NO_TMA
             auto issue = [&](int stage, int e0, int d) {
                 if (d <= MAXD && d > 0 && lane == 0) {
                     uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
@@ -656,7 +658,7 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
             for (; c < g.m; c += kWarps, stage ^= 1) {
                 const int e0 = e0c, d = dc;
                 e0c = e0n; dc = dn;
-#ifdef LDPC_I8_TMA
+#ifndef LDPC_I8_NO_TMA
                 if (c + kWarps < g.m) {
                     issue(stage ^ 1, e0c, dc);
                     row_of(c + 2 * kWarps, e0n, dn);
