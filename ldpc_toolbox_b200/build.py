@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libldpc_toolbox.so")
 
-CU_SOURCES = ["ber.cu", "capi.cu", "decoder.cu", "flood_i8.cu", "generic_bp.cu", "ingest.cu"]
+CU_SOURCES = ["ber.cu", "capi.cu", "decoder.cu", "flood_i8.cu", "generic_bp.cu", "ingest.cu", "layered_smem.cu"]
 CPP_SOURCES = ["host.cpp"]
 
 # experiment knobs for flood_i8.cu (warps per CTA, min CTAs per SM); empty = the defaults in the source
@@ -63,13 +63,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     log = []
     # the image exports CXX=/opt/gcc/bin/g++ (a wrapper); nvcc must use the system host compiler
     ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
-    for src in CU_SOURCES + CPP_SOURCES:
+    def compile_one(src):
         obj = os.path.join(OUT_DIR, src.rsplit(".", 1)[0] + ".o")
         cmd = [nvcc] + ccbin + NVCC_FLAGS + ["-x", "cu" if src.endswith(".cu") else "c++", "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-        if r.returncode != 0:
-            sys.stderr.write(log[-1])
+        return obj, "$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr, r.returncode
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:      # one nvcc per translation unit
+        results = list(ex.map(compile_one, CU_SOURCES + CPP_SOURCES))
+    for (obj, text, rc), src in zip(results, CU_SOURCES + CPP_SOURCES):
+        log.append(text)
+        if rc != 0:
+            sys.stderr.write(text)
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
     cmd = [nvcc] + ccbin + ["-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]

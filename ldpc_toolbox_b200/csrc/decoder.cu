@@ -100,6 +100,16 @@ public:
         dg_.row_ptr = d_row_ptr_.p; dg_.col_idx = d_col_idx_.p; dg_.col_ptr = d_col_ptr_.p; dg_.col_edge = d_col_edge_.p;
         if (kind_ == Kind::FloodI8 && !build_var_classes()) return false;
         if (kind_ == Kind::Layered && !build_levels()) return false;
+        if (kind_ == Kind::Layered) {
+            // K3q (frame per CTA, posteriors in shared memory) when they fit and the level schedule is wide
+            int path = opt.layered_path;
+            if (const char* e = getenv("LDPC_B200_LAYERED")) path = !strcmp(e, "tile") ? 1 : (!strcmp(e, "smem") ? 2 : path);
+            const size_t need = layered_smem_bytes(g_.n, impl_.dtype == Dtype::F64, impl_.dtype == Dtype::I8) + 1024;
+            const bool fits = need <= (size_t)prop.sharedMemPerBlockOptin;
+            const bool wide = num_levels_ > 0 && g_.m / num_levels_ >= 16;
+            use_smem_layered_ = fits && (path == 2 || (path == 0 && wide));
+            if (use_smem_layered_ && !build_ell()) return false;
+        }
         LDPC_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
         for (auto& e : ev_) LDPC_CUDA_CHECK(cudaEventCreate(&e));
         max_tiles_opt_ = opt.max_tiles;
@@ -217,6 +227,7 @@ private:
         if (kind_ == Kind::FloodI8) return E * kLanes * 5 + n * kLanes * 4 + 2 * n * kLanes;
         const size_t s = elem_size();
         if (kind_ == Kind::FloodFloat) return E * kTileFrames * s + E * kLanes + n * kTileFrames * s + 2 * n * kLanes;
+        if (use_smem_layered_) return ell_size_ * kTileFrames * s;
         const size_t qs = impl_.dtype == Dtype::I8 ? 2 : s;
         return E * kTileFrames * s + n * kTileFrames * qs + 2 * n * kLanes;
     }
@@ -288,7 +299,69 @@ private:
         std::vector<int> fill(level_ptr.begin(), level_ptr.end() - 1);
         for (int r = 0; r < g_.m; ++r) level_rows[(size_t)fill[(size_t)row_level[(size_t)r]]++] = r;
         num_levels_ = num_levels;
+        h_level_ptr_ = level_ptr;
+        h_level_rows_ = level_rows;
         return d_level_ptr_.upload(level_ptr) && d_level_rows_.upload(level_rows);
+    }
+
+    // ELL layout of the level schedule for layered_smem.cu
+    bool build_ell() {
+        std::vector<int> row_base((size_t)g_.m), row_stride((size_t)g_.m), row_deg((size_t)g_.m), ell_col;
+        size_t off = 0;
+        int widest = 1;
+        for (int l = 0; l < num_levels_; ++l) {
+            const int r0 = h_level_ptr_[(size_t)l], r1 = h_level_ptr_[(size_t)l + 1], nrows = r1 - r0;
+            int maxd = 0;
+            for (int i = r0; i < r1; ++i) {
+                const int c = h_level_rows_[(size_t)i];
+                maxd = std::max(maxd, g_.row_ptr[(size_t)c + 1] - g_.row_ptr[(size_t)c]);
+            }
+            ell_col.resize(off + (size_t)maxd * nrows, 0);
+            for (int i = r0; i < r1; ++i) {
+                const int c = h_level_rows_[(size_t)i], e0 = g_.row_ptr[(size_t)c], d = g_.row_ptr[(size_t)c + 1] - e0;
+                row_base[(size_t)i] = (int)(off + (size_t)(i - r0));
+                row_stride[(size_t)i] = nrows;
+                row_deg[(size_t)i] = d;
+                for (int j = 0; j < d; ++j) ell_col[off + (size_t)j * nrows + (size_t)(i - r0)] = g_.col_idx[(size_t)e0 + j];
+            }
+            off += (size_t)maxd * nrows;
+            widest = std::max(widest, nrows);
+        }
+        if (off > 0x7fffffffu) { set_last_error("level schedule too large"); return false; }
+        ell_size_ = std::max<size_t>(off, 1);
+        smem_threads_ = std::min(512, std::max(64, (widest + 31) / 32 * 32));
+        if (!d_row_base_.upload(row_base) || !d_row_stride_.upload(row_stride) || !d_row_deg_.upload(row_deg) || !d_ell_col_.upload(ell_col))
+            return false;
+        sg_.n = g_.n; sg_.m = g_.m; sg_.num_levels = num_levels_; sg_.level_ptr = d_level_ptr_.p; sg_.row_base = d_row_base_.p;
+        sg_.row_stride = d_row_stride_.p; sg_.row_deg = d_row_deg_.p; sg_.ell_col = d_ell_col_.p; sg_.ell_size = ell_size_;
+        return true;
+    }
+
+    bool run_chunk_smem_layered(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
+                                size_t out_len, size_t out_stride, int32_t* d_iters, cudaStream_t s, cudaEvent_t after_ingest) {
+        const size_t esz = layered_smem_rcv_elem(impl_.dtype == Dtype::F64, impl_.dtype == Dtype::I8);
+        if (!d_msg_.ensure(nf * ell_size_ * esz)) return false;
+        ws_bytes_ = d_msg_.count;
+        cudaEventRecord(ev_[0], s);
+        cudaEventRecord(ev_[1], s);
+        LayeredSmemLaunch L{};
+        L.graph = sg_;
+        L.rule = impl_.rule == Rule::Phi ? kPhi : impl_.rule == Rule::Tanh ? kTanh : impl_.rule == Rule::Minstarapprox ? kMinstarapprox : kAminstar;
+        L.is_f64 = impl_.dtype == Dtype::F64; L.is_i8 = impl_.dtype == Dtype::I8; L.hardlimit = impl_.hardlimit;
+        L.threads = smem_threads_;
+        L.llrs = d_llrs; L.in_f64 = is_f64; L.llrs_len = llrs_len; L.nframes = nf; L.src_map = punct_ ? d_src_map_.p : nullptr;
+        L.rcv = d_msg_.p; L.out = d_out; L.out_len = out_len; L.out_stride = out_stride; L.iters = d_iters;
+        L.max_iter = panics_ ? 0 : (int)std::min<uint32_t>(max_it, 0x7ffffff0u);
+        if (!launch_layered_smem(L, s)) return false;
+        if (after_ingest) cudaEventRecord(after_ingest, s);     // the caller's LLR buffer is consumed by the decode kernel itself
+        cudaEventRecord(ev_[2], s);
+        if (panics_ && max_it > 0) {
+            if (!launch_mark_panics(d_iters, nf, s)) return false;
+        }
+        cudaEventRecord(ev_[3], s);
+        stats_.kernel_launches += 1;
+        timed_ = true;
+        return true;
     }
 
     bool ensure_workspace(size_t tiles, int nw) {
@@ -312,6 +385,7 @@ private:
 
     bool run_chunk(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
                    size_t out_len, size_t out_stride, int32_t* d_iters, cudaStream_t s, cudaEvent_t after_ingest = nullptr) {
+        if (use_smem_layered_) return run_chunk_smem_layered(d_llrs, is_f64, llrs_len, nf, max_it, d_out, out_len, out_stride, d_iters, s, after_ingest);
         const int nw = pick_nw(nf);
         const size_t tf = (size_t)kTileFrames * nw;
         const int tiles = (int)((nf + tf - 1) / tf);
@@ -393,6 +467,12 @@ private:
     DevBuf<int> d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_src_map_, d_var_list_, d_var_edges_, d_level_ptr_, d_level_rows_;
     VarClasses vc_{};
     int num_levels_ = 0;
+    bool use_smem_layered_ = false;
+    std::vector<int> h_level_ptr_, h_level_rows_;
+    DevBuf<int> d_row_base_, d_row_stride_, d_row_deg_, d_ell_col_;
+    LayeredSmemGraph sg_{};
+    size_t ell_size_ = 1;
+    int smem_threads_ = 256;
     DevBuf<uint8_t> d_msg_, d_inq_;
     DevBuf<uint8_t> d_hbit_, d_hard_, d_final_, d_stage_in_[2], d_stage_out_[2];
     DevBuf<int32_t> d_iters_tile_, d_stage_iters_[2];

@@ -56,6 +56,7 @@ struct DecoderOptions {
     int device = -1;                 // -1: current device
     int max_tiles = 0;               // frames per launch / 128; 0: automatic (whole waves of CTAs that fit in free HBM)
     int words_per_lane = 0;          // int8 decoders: 1 = 128-frame tiles, 4 = 512-frame tiles, 0 = by batch size
+    int layered_path = 0;            // layered decoders: 0 = automatic, 1 = frame-interleaved tiles (K3), 2 = frame per CTA (K3q)
 };
 
 // DecoderFactory::build_decoder.  Returns nullptr and sets last_error() on failure.

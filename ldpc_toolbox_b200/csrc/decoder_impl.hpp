@@ -97,4 +97,36 @@ bool launch_flood_float(const GenericLaunch& L, cudaStream_t stream);
 bool launch_layered(const GenericLaunch& L, cudaStream_t stream);
 int generic_max_row_degree();
 
+// ---- layered_smem.cu ---------------------------------------------------------------------------
+// Level schedule in ELL order (host-built once per code): rows are listed level by level; the slots
+// of a level form a block [max degree of the level][rows of the level], so slot j of consecutive
+// rows of a level is contiguous.  Rcv of a frame uses the same indexing.
+struct LayeredSmemGraph {
+    int n, m, num_levels;
+    const int* level_ptr;    // num_levels+1, into the level-ordered row arrays below
+    const int* row_base;     // m: ELL index of slot 0 of the row
+    const int* row_stride;   // m: rows in the row's level (distance between slots)
+    const int* row_deg;      // m
+    const int* ell_col;      // ell_size: variable of each slot (padding slots are never read)
+    size_t ell_size;
+};
+struct LayeredSmemLaunch {
+    LayeredSmemGraph graph;
+    int rule;
+    bool is_f64, is_i8, hardlimit;
+    int threads;             // CTA size (multiple of 32)
+    const void* llrs;        // device, caller layout [nframes][llrs_len]
+    bool in_f64;
+    size_t llrs_len, nframes;
+    const int* src_map;      // depuncture map or null
+    void* rcv;               // [nframes][ell_size] check->variable messages (f32 / f64 / int8)
+    uint8_t* out;            // device, [nframes][out_stride]
+    size_t out_len, out_stride;
+    int32_t* iters;          // device, [nframes]
+    int max_iter;
+};
+bool launch_layered_smem(const LayeredSmemLaunch& L, cudaStream_t stream);
+size_t layered_smem_bytes(int n, bool is_f64, bool is_i8);
+size_t layered_smem_rcv_elem(bool is_f64, bool is_i8);
+
 }  // namespace ldpc

@@ -30,6 +30,23 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // 4 bytes of 0/1 (one per frame) -> 4-bit mask
 __device__ __forceinline__ uint32_t pack_bits4(uint32_t bytes01) { return (bytes01 * 0x01020408u) >> 24; }
 
+// input_llr_quantize of the int8 arithmetics (reference src/decoder/arithmetic.rs:690-699): x8, saturate
+// at +-127, round half away from zero, NaN -> 0
+__device__ __forceinline__ int quantize_i8(double llr) {
+    double x = 8.0 * llr;
+    if (x >= 127.0) return 127;
+    if (x <= -127.0) return -127;
+    if (x != x) return 0;              // Rust `as i8` maps NaN to 0
+    return (int)round(x);              // f64::round: half away from zero
+}
+__device__ __forceinline__ int quantize_i8(float llr) {
+    float x = 8.0f * llr;              // exact scaling: same value as the reference's f64 product
+    if (x >= 127.0f) return 127;
+    if (x <= -127.0f) return -127;
+    if (x != x) return 0;
+    return (int)roundf(x);
+}
+
 #define LDPC_CUDA_CHECK(expr)                                                                   \
     do {                                                                                        \
         cudaError_t _e = (expr);                                                                \

@@ -790,11 +790,8 @@ void launch_one(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t str
     constexpr int MAXD = NW == 1 ? 10 : 8;
     constexpr size_t stage = (size_t)MAXD * kLanes * NW * 4 + (size_t)MAXD * kLanes * sizeof(typename HBitsT<NW>::type);
     constexpr size_t smem = (size_t)kWarps * 2 * stage;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(flood_i8_kernel<NW, AMIN, HLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    // per device and cheap: set on every launch (one process may drive several GPUs)
+    cudaFuncSetAttribute(flood_i8_kernel<NW, AMIN, HLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     flood_i8_kernel<NW, AMIN, HLIM><<<dim3((unsigned)L.num_tiles), dim3(kWarps * 32), smem, stream>>>(p);
 }
 

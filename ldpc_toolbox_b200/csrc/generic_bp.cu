@@ -93,6 +93,30 @@ struct FloodFloatParams {
     int max_iter;
 };
 
+// One check of a 128-frame tile.  DT > 0: compile-time degree, everything in registers.  The four
+// frames of a lane are processed one after the other by rotating the components of the 4-vectors
+// (component 0 is consumed, the result re-enters as component 3), so the frame loop stays rolled
+// without ever indexing a register array with a run-time value.
+template <class F, int RULE, int DT>
+__device__ __forceinline__ void flood_check_row(F* __restrict__ msg, size_t e0, int d_rt, int lane) {
+    constexpr int CAP = DT > 0 ? DT : kRuleMaxD;
+    const int d = DT > 0 ? DT : d_rt;
+    V4<F> xs[CAP];
+#pragma unroll
+    for (int j = 0; j < d; ++j) xs[j] = ld4<F>(msg, e0 + j, lane);
+#pragma unroll 1
+    for (int f = 0; f < 4; ++f) {
+        F x[CAP], out[CAP], scratch[CAP];
+#pragma unroll
+        for (int j = 0; j < d; ++j) x[j] = xs[j].v[0];
+        check_rule_float<F, RULE, DT>(x, d, out, scratch);
+#pragma unroll
+        for (int j = 0; j < d; ++j) { xs[j].v[0] = xs[j].v[1]; xs[j].v[1] = xs[j].v[2]; xs[j].v[2] = xs[j].v[3]; xs[j].v[3] = out[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < d; ++j) st4<F>(msg, e0 + j, lane, xs[j]);
+}
+
 template <class F, int RULE>
 __global__ void __launch_bounds__(kGWarps * 32) flood_float_kernel(FloodFloatParams<F> p) {
     __shared__ StopState st;
@@ -128,16 +152,13 @@ __global__ void __launch_bounds__(kGWarps * 32) flood_float_kernel(FloodFloatPar
             for (int j = 0; j < d; ++j) hb ^= hbit[(size_t)(e0 + j) * kLanes + lane];
             synd |= hb;
             if (last || d == 0) continue;
-            V4<F> xs[kRuleMaxD];
-            for (int j = 0; j < d; ++j) xs[j] = ld4<F>(msg, (size_t)(e0 + j), lane);
-#pragma unroll 1
-            for (int f = 0; f < 4; ++f) {
-                F x[kRuleMaxD], out[kRuleMaxD], scratch[kRuleMaxD];
-                for (int j = 0; j < d; ++j) x[j] = xs[j].v[f];
-                check_rule_float<F, RULE>(x, d, out, scratch);
-                for (int j = 0; j < d; ++j) xs[j].v[f] = out[j];
+#define LDPC_CHK_CASE(D_) case D_: flood_check_row<F, RULE, D_>(msg, (size_t)e0, d, lane); break;
+            switch (d) {
+                LDPC_CHK_CASE(1) LDPC_CHK_CASE(2) LDPC_CHK_CASE(3) LDPC_CHK_CASE(4) LDPC_CHK_CASE(5) LDPC_CHK_CASE(6)
+                LDPC_CHK_CASE(7) LDPC_CHK_CASE(8) LDPC_CHK_CASE(9) LDPC_CHK_CASE(10)
+                default: flood_check_row<F, RULE, 0>(msg, (size_t)e0, d, lane); break;
             }
-            for (int j = 0; j < d; ++j) st4<F>(msg, (size_t)(e0 + j), lane, xs[j]);
+#undef LDPC_CHK_CASE
         }
         if (synd) atomicOr(&st.unsat[lane], synd);
         __syncthreads();
@@ -229,6 +250,62 @@ __device__ __forceinline__ uint32_t syndrome_pass(const DeviceGraph& g, int warp
     return synd;
 }
 
+// One row of a 128-frame tile (see flood_check_row for the component rotation).
+template <class F, int RULE, bool IS_I8, bool HLIM, int DT, class Q, class R>
+__device__ __forceinline__ void layered_tile_row(Q* __restrict__ qv, R* __restrict__ rcv, const int* __restrict__ col_idx, int e0,
+                                                 int d_rt, int lane, const I8Tables& tb) {
+    constexpr int CAP = DT > 0 ? DT : kRuleMaxD;
+    const int d = DT > 0 ? DT : d_rt;
+    int col[CAP];
+    V4<Q> qs[CAP];
+    V4<R> rs[CAP];
+#pragma unroll
+    for (int j = 0; j < d; ++j) col[j] = __ldg(col_idx + e0 + j);
+#pragma unroll
+    for (int j = 0; j < d; ++j) {
+        qs[j] = ld4<Q>(qv, (size_t)col[j], lane);
+        rs[j] = ld4<R>(rcv, (size_t)(e0 + j), lane);
+    }
+#pragma unroll 1
+    for (int f = 0; f < 4; ++f) {
+        Q qn[CAP];
+        R rn[CAP];
+        if (IS_I8) {
+            int x[CAP], out[CAP];
+#pragma unroll
+            for (int j = 0; j < d; ++j) x[j] = i8_clip((int)qs[j].v[0] - (int)rs[j].v[0]);   // arithmetic.rs:775, :1204
+            check_rule_i8<RULE, HLIM, DT>(x, d, out, tb);
+#pragma unroll
+            for (int j = 0; j < d; ++j) {
+                // :797-800 and :1243-1256 are the same integer update
+                qn[j] = (Q)((int)qs[j].v[0] - (int)rs[j].v[0] + out[j]);
+                rn[j] = (R)out[j];
+            }
+        } else {
+            F x[CAP], out[CAP], scratch[CAP];
+#pragma unroll
+            for (int j = 0; j < d; ++j) x[j] = (F)qs[j].v[0] - (F)rs[j].v[0];
+            check_rule_float<F, RULE, DT>(x, d, out, scratch);
+#pragma unroll
+            for (int j = 0; j < d; ++j) {
+                if (RULE == kPhi || RULE == kAminstar) qn[j] = (Q)(x[j] + out[j]);                      // :290, :1064
+                else qn[j] = (Q)((F)qs[j].v[0] + (out[j] - (F)rs[j].v[0]));                             // :423, :571
+                rn[j] = (R)out[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < d; ++j) {
+            qs[j].v[0] = qs[j].v[1]; qs[j].v[1] = qs[j].v[2]; qs[j].v[2] = qs[j].v[3]; qs[j].v[3] = qn[j];
+            rs[j].v[0] = rs[j].v[1]; rs[j].v[1] = rs[j].v[2]; rs[j].v[2] = rs[j].v[3]; rs[j].v[3] = rn[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < d; ++j) {
+        st4<Q>(qv, (size_t)col[j], lane, qs[j]);
+        st4<R>(rcv, (size_t)(e0 + j), lane, rs[j]);
+    }
+}
+
 template <class F, int RULE, bool IS_I8, bool HLIM>
 __global__ void __launch_bounds__(kGWarps * 32)
 layered_kernel(LayeredParams<typename std::conditional<IS_I8, int16_t, F>::type, typename std::conditional<IS_I8, int8_t, F>::type> p) {
@@ -304,38 +381,13 @@ layered_kernel(LayeredParams<typename std::conditional<IS_I8, int16_t, F>::type,
                 const int c = __ldg(p.level_rows + ri);
                 const int e0 = __ldg(g.row_ptr + c), d = __ldg(g.row_ptr + c + 1) - e0;
                 if (d == 0) continue;
-                V4<Q> qs[kRuleMaxD];
-                V4<R> rs[kRuleMaxD];
-                for (int j = 0; j < d; ++j) {
-                    qs[j] = ld4<Q>(qv, (size_t)__ldg(g.col_idx + e0 + j), lane);
-                    rs[j] = ld4<R>(rcv, (size_t)(e0 + j), lane);
+#define LDPC_ROW_CASE(D_) case D_: layered_tile_row<F, RULE, IS_I8, HLIM, D_, Q, R>(qv, rcv, g.col_idx, e0, d, lane, tb); break;
+                switch (d) {
+                    LDPC_ROW_CASE(1) LDPC_ROW_CASE(2) LDPC_ROW_CASE(3) LDPC_ROW_CASE(4) LDPC_ROW_CASE(5) LDPC_ROW_CASE(6)
+                    LDPC_ROW_CASE(7) LDPC_ROW_CASE(8) LDPC_ROW_CASE(9) LDPC_ROW_CASE(10)
+                    default: layered_tile_row<F, RULE, IS_I8, HLIM, 0, Q, R>(qv, rcv, g.col_idx, e0, d, lane, tb); break;
                 }
-#pragma unroll 1
-                for (int f = 0; f < 4; ++f) {
-                    if (IS_I8) {
-                        int x[kRuleMaxD], out[kRuleMaxD];
-                        for (int j = 0; j < d; ++j) x[j] = i8_clip((int)qs[j].v[f] - (int)rs[j].v[f]);   // arithmetic.rs:775, :1204
-                        check_rule_i8<RULE, HLIM>(x, d, out, tb);
-                        for (int j = 0; j < d; ++j) {
-                            // :797-800 and :1243-1256 are the same integer update
-                            qs[j].v[f] = (Q)((int)qs[j].v[f] - (int)rs[j].v[f] + out[j]);
-                            rs[j].v[f] = (R)out[j];
-                        }
-                    } else {
-                        F x[kRuleMaxD], out[kRuleMaxD], scratch[kRuleMaxD];
-                        for (int j = 0; j < d; ++j) x[j] = (F)qs[j].v[f] - (F)rs[j].v[f];
-                        check_rule_float<F, RULE>(x, d, out, scratch);
-                        for (int j = 0; j < d; ++j) {
-                            if (RULE == kPhi || RULE == kAminstar) qs[j].v[f] = (Q)(x[j] + out[j]);            // :290, :1064
-                            else qs[j].v[f] = (Q)((F)qs[j].v[f] + (out[j] - (F)rs[j].v[f]));                   // :423, :571
-                            rs[j].v[f] = (R)out[j];
-                        }
-                    }
-                }
-                for (int j = 0; j < d; ++j) {
-                    st4<Q>(qv, (size_t)__ldg(g.col_idx + e0 + j), lane, qs[j]);
-                    st4<R>(rcv, (size_t)(e0 + j), lane, rs[j]);
-                }
+#undef LDPC_ROW_CASE
             }
             __syncthreads();
         }

@@ -18,21 +18,6 @@ namespace {
 constexpr int kChunk = 32;       // variables per CTA
 constexpr int kIngestWarps = 8;
 
-__device__ __forceinline__ int quantize_i8(double llr) {
-    double x = 8.0 * llr;
-    if (x >= 127.0) return 127;
-    if (x <= -127.0) return -127;
-    if (x != x) return 0;              // Rust `as i8` maps NaN to 0
-    return (int)round(x);              // f64::round: half away from zero
-}
-__device__ __forceinline__ int quantize_i8(float llr) {
-    float x = 8.0f * llr;              // exact scaling: same value as the reference's f64 product
-    if (x >= 127.0f) return 127;
-    if (x <= -127.0f) return -127;
-    if (x != x) return 0;
-    return (int)roundf(x);
-}
-
 // NW = words per lane of the decoder tile: a tile holds TF = 128*NW frames, stored per node as TF
 // consecutive values (frame index = lane*4*NW + word*4 + byte).
 template <typename TIn, int MODE, int NW>   // MODE 0: int8, 1: f32, 2: f64, 3: int16 decoder state

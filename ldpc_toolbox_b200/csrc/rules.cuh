@@ -44,9 +44,12 @@ template <> struct FMath<double> {
 };
 
 // ---- float rules: x in, out out (may not alias), scratch has room for d values -----------------
-template <class F, int RULE>
-__device__ __forceinline__ void check_rule_float(const F* x, int d, F* out, F* scratch) {
+// DT > 0: the degree is the compile-time constant DT (every loop unrolls and x / out / scratch stay
+// in registers); DT == 0: run-time degree d_rt.
+template <class F, int RULE, int DT = 0>
+__device__ __forceinline__ void check_rule_float(const F* x, int d_rt, F* out, F* scratch) {
     using M = FMath<F>;
+    const int d = DT > 0 ? DT : d_rt;
     if (RULE == kPhi) {
         auto phi = [](F v) {                                   // arithmetic.rs:180-185
             v = M::max_(v, F(1e-30));
@@ -54,27 +57,27 @@ __device__ __forceinline__ void check_rule_float(const F* x, int d, F* out, F* s
         };
         unsigned sign = 0;
         F sum = F(0);
-        for (int i = 0; i < d; ++i) {
+        _Pragma("unroll") for (int i = 0; i < d; ++i) {
             F p = phi(M::abs_(x[i]));
             scratch[i] = p;
             sum += p;
             if (x[i] < F(0)) sign ^= 1u;
         }
-        for (int i = 0; i < d; ++i) {
+        _Pragma("unroll") for (int i = 0; i < d; ++i) {
             F y = phi(sum - scratch[i]);
             unsigned s = x[i] < F(0) ? (sign ^ 1u) : sign;
             out[i] = s == 0 ? y : -y;
         }
     } else if (RULE == kTanh) {
         const F c = M::tanh_clamp();
-        for (int i = 0; i < d; ++i) {
+        _Pragma("unroll") for (int i = 0; i < d; ++i) {
             F h = F(0.5) * x[i];
             h = h < -c ? -c : (h > c ? c : h);                 // Rust clamp (NaN propagates)
             scratch[i] = M::tanh_(h);
         }
-        for (int j = 0; j < d; ++j) {
+        _Pragma("unroll") for (int j = 0; j < d; ++j) {
             F prod = F(1);
-            for (int i = 0; i < d; ++i)
+            _Pragma("unroll") for (int i = 0; i < d; ++i)
                 if (i != j) prod *= scratch[i];
             out[j] = F(2) * M::atanh_(prod);
         }
@@ -84,13 +87,13 @@ __device__ __forceinline__ void check_rule_float(const F* x, int d, F* out, F* s
         };
         // shared prefix P_j = fold(|x_0| .. |x_{j-1}|); the remaining terms are folded per output
         F P = F(0);
-        for (int j = 0; j < d; ++j) {
+        _Pragma("unroll") for (int j = 0; j < d; ++j) {
             unsigned sign = 0;
-            for (int i = 0; i < d; ++i)
+            _Pragma("unroll") for (int i = 0; i < d; ++i)
                 if (i != j && x[i] < F(0)) sign ^= 1u;
             F acc = P;
             bool have = j > 0;
-            for (int i = j + 1; i < d; ++i) {
+            _Pragma("unroll") for (int i = j + 1; i < d; ++i) {
                 F a = M::abs_(x[i]);
                 acc = have ? g(a, acc) : a;
                 have = true;
@@ -105,14 +108,14 @@ __device__ __forceinline__ void check_rule_float(const F* x, int d, F* out, F* s
         };
         int arg = 0;
         F best = M::abs_(x[0]);
-        for (int i = 1; i < d; ++i) {
+        _Pragma("unroll") for (int i = 1; i < d; ++i) {
             F a = M::abs_(x[i]);
             if (a < best) { best = a; arg = i; }               // first minimum
         }
         unsigned sign = 0;
         bool have = false;
         F delta = F(0);
-        for (int j = 0; j < d; ++j) {
+        _Pragma("unroll") for (int j = 0; j < d; ++j) {
             if (x[j] < F(0)) sign ^= 1u;
             if (j != arg) {
                 F a = M::abs_(x[j]);
@@ -120,8 +123,8 @@ __device__ __forceinline__ void check_rule_float(const F* x, int d, F* out, F* s
                 have = true;
             }
         }
-        F d2 = h(delta, M::abs_(x[arg]));
-        for (int j = 0; j < d; ++j) {
+        F d2 = h(delta, best);                                 // best == |x[arg]|
+        _Pragma("unroll") for (int j = 0; j < d; ++j) {
             F mag = j == arg ? delta : d2;
             bool neg = (sign != 0) ^ (x[j] < F(0));
             out[j] = neg ? -mag : mag;
@@ -149,19 +152,20 @@ __device__ __forceinline__ void i8_tables_init(I8Tables& tb) {
 
 __device__ __forceinline__ int i8_clip(int x) { return x >= 127 ? 127 : (x <= -127 ? -127 : x); }   // arithmetic.rs:609-617
 
-template <int RULE, bool HLIM>
-__device__ __forceinline__ void check_rule_i8(const int* x, int d, int* out, const I8Tables& tb) {
+template <int RULE, bool HLIM, int DT = 0>
+__device__ __forceinline__ void check_rule_i8(const int* x, int d_rt, int* out, const I8Tables& tb) {
+    const int d = DT > 0 ? DT : d_rt;
     auto hl = [](int m) { return HLIM ? (m >= 100 ? 127 : m) : m; };
     if (RULE == kMinstarapprox) {
         auto g = [&](int a, int acc) { return max(acc + (int)tb.U[a - acc + 127], 0); };
         int P = 0;
-        for (int j = 0; j < d; ++j) {
+        _Pragma("unroll") for (int j = 0; j < d; ++j) {
             unsigned sign = 0;
-            for (int i = 0; i < d; ++i)
+            _Pragma("unroll") for (int i = 0; i < d; ++i)
                 if (i != j && x[i] < 0) sign ^= 1u;
             int acc = P;
             bool have = j > 0;
-            for (int i = j + 1; i < d; ++i) {
+            _Pragma("unroll") for (int i = j + 1; i < d; ++i) {
                 int a = abs(x[i]);
                 acc = have ? g(a, acc) : a;
                 have = true;
@@ -174,14 +178,14 @@ __device__ __forceinline__ void check_rule_i8(const int* x, int d, int* out, con
     } else {
         auto h = [&](int a, int b) { return max(b + (int)tb.U[a - b + 127] + (int)tb.Tp[min(a + b, 127)], 0); };
         int arg = 0, best = abs(x[0]);
-        for (int i = 1; i < d; ++i) {
+        _Pragma("unroll") for (int i = 1; i < d; ++i) {
             int a = abs(x[i]);
             if (a < best) { best = a; arg = i; }
         }
         unsigned sign = 0;
         bool have = false;
         int delta = 0;
-        for (int j = 0; j < d; ++j) {
+        _Pragma("unroll") for (int j = 0; j < d; ++j) {
             if (x[j] < 0) sign ^= 1u;
             if (j != arg) {
                 int a = abs(x[j]);
@@ -189,9 +193,9 @@ __device__ __forceinline__ void check_rule_i8(const int* x, int d, int* out, con
                 have = true;
             }
         }
-        int d2 = hl(h(delta, abs(x[arg])));
+        int d2 = hl(h(delta, best));                           // best == |x[arg]|
         int d1 = hl(delta);
-        for (int j = 0; j < d; ++j) {
+        _Pragma("unroll") for (int j = 0; j < d; ++j) {
             int mag = j == arg ? d1 : d2;
             bool neg = (sign != 0) ^ (x[j] < 0);
             out[j] = neg ? -mag : mag;

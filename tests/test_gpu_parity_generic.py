@@ -37,12 +37,40 @@ def small_code_stimulus(seed, dtype=np.float32):
     return cases
 
 
+@pytest.mark.parametrize("path", ["tile", "smem"])
 @pytest.mark.parametrize("impl", HL_I8)
-def test_layered_i8_bit_exact(oracle, impl):
+def test_layered_i8_bit_exact(oracle, impl, path, monkeypatch):
+    """Both layered kernels: K3 (frame-interleaved tiles) and K3q (frame per CTA, posteriors in shared memory)."""
+    monkeypatch.setenv("LDPC_B200_LAYERED", path)
     for alist, llrs in small_code_stimulus(21):
         nbad, its, _ = run_pair(oracle, alist, impl, llrs, 12)
         assert nbad == 0, impl
         assert (its > 0).any()
+
+
+@pytest.mark.parametrize("impl", HL_FLOAT)
+def test_layered_float_smem_path_small_codes(oracle, impl, monkeypatch):
+    monkeypatch.setenv("LDPC_B200_LAYERED", "smem")
+    total = bad = 0
+    for alist, llrs in small_code_stimulus(23, np.float64 if impl.endswith("f64") else np.float32):
+        nbad, its, rits = run_pair(oracle, alist, impl, llrs, 12)
+        bad += nbad
+        total += len(its)
+    assert bad <= (2 if impl.endswith("f64") else 8), f"{impl}: {bad} of {total} frames differ from the CPU checker"
+
+
+def test_layered_smem_punctured_f64_input_and_zero_iterations(oracle, monkeypatch):
+    """K3q reads the caller's LLRs itself: depuncturing, f64 input, max_iterations = 0 and output_len < n."""
+    monkeypatch.setenv("LDPC_B200_LAYERED", "smem")
+    alist = codes.alist_for("ar4ja:1/2:1024")
+    rng = np.random.default_rng(35)
+    enc = oracle.encoder(alist, "1,1,1,1,0")
+    msgs = rng.integers(0, 2, size=(96, 1024), dtype=np.uint8)
+    tx = np.stack([enc.encode(m, 2048) for m in msgs])
+    llrs = helpers.awgn_llrs(rng, tx, helpers.sigma_for(1.8, 0.5), np.float64)
+    for impl, iters in (("HLMinstarapproxi8", 30), ("HLAminstari8", 0), ("HLPhif64", 20)):
+        nbad, its, rits = run_pair(oracle, alist, impl, llrs, iters, puncturing="1,1,1,1,0", out_len=1024)
+        assert nbad <= (1 if impl.endswith("f64") else 0), (impl, nbad)
 
 
 @pytest.mark.parametrize("impl", FLOAT_FLOOD + HL_FLOAT)
