@@ -17,7 +17,10 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libldpc_toolbox.so")
 
-CU_SOURCES = ["ber.cu", "capi.cu", "decoder.cu", "flood_i8.cu", "generic_bp.cu", "ingest.cu", "layered_smem.cu"]
+# heavy kernels first: one nvcc per translation unit runs in parallel (see build())
+CU_SOURCES = ["flood_float_f64.cu", "flood_float_f32.cu", "layered_smem_f64.cu", "layered_smem_f32.cu", "layered_tile_f64.cu",
+              "layered_tile_f32.cu", "flood_i8.cu", "layered_tile_i8.cu", "layered_smem_i8.cu", "ber.cu", "capi.cu", "decoder.cu",
+              "generic_bp.cu", "ingest.cu", "layered_smem.cu"]
 CPP_SOURCES = ["host.cpp"]
 
 # experiment knobs for flood_i8.cu (warps per CTA, min CTAs per SM); empty = the defaults in the source

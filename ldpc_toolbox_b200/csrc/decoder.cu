@@ -420,6 +420,9 @@ private:
             gl.msg = d_msg_.p; gl.hbit = d_hbit_.p; gl.in = d_inq_.p; gl.in_out_q = d_inq_.p;
             gl.raw0 = d_hard_.p; gl.final_hard = d_final_.p; gl.iters = d_iters_tile_.p; gl.max_iter = max_iter;
             gl.level_ptr = d_level_ptr_.p; gl.level_rows = d_level_rows_.p; gl.num_levels = num_levels_;
+            gl.cluster = 1;
+            while (gl.cluster < 8 && tiles * gl.cluster * 2 <= 2 * sm_count_) gl.cluster *= 2;      // up to ~2 CTAs per SM
+            if (const char* e = getenv("LDPC_B200_CLUSTER")) gl.cluster = atoi(e);
             if (!(kind_ == Kind::FloodFloat ? launch_flood_float(gl, s) : launch_layered(gl, s))) return false;
         }
         cudaEventRecord(ev_[2], s);

@@ -92,6 +92,7 @@ struct GenericLaunch {
     const int* level_ptr;   // layered: level schedule
     const int* level_rows;
     int num_levels;
+    int cluster;            // flooding: CTAs per tile (thread-block cluster of 1, 2, 4 or 8), small batches fill the GPU this way
 };
 bool launch_flood_float(const GenericLaunch& L, cudaStream_t stream);
 bool launch_layered(const GenericLaunch& L, cudaStream_t stream);

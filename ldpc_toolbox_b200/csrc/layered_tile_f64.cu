@@ -1,0 +1,6 @@
+// ldpc_toolbox_b200/csrc/layered_tile_f64.cu — one translation unit per arithmetic type so the kernels build in parallel.
+#include "layered_tile_impl.cuh"
+
+namespace ldpc {
+bool launch_layered_tile_f64(const GenericLaunch& L, cudaStream_t s) { return launch_layered_t<double, false>(L, s); }
+}  // namespace ldpc
