@@ -40,6 +40,16 @@ def algorithmic_bytes(total_iterations: int, frames: int) -> float:
     return total_iterations * 4.0 * E * 1 + frames * (N * 4 + N / 8)
 
 
+def measured_traffic(total_iterations: int):
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu capture
+    (dram__bytes_read.sum + dram__bytes_write.sum), scaled by frame-iterations when the launch differs."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_d_traffic.json")))
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * total_iterations / (t["frames"] * t["iterations"])
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -223,7 +233,7 @@ def run_ours(args):
                    "l2": "inputs (%.1f GB LLRs + %.1f GB message state per step) exceed the 126 MB L2" % (frames * N * 4 / 1e9, frames * E / 1e9),
                    "edge_msgs_per_s": round(2.0 * E * total_iters * world / (ms_total / args.steps * 1e-3), 1)},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": None, "kernel": "flood_i8_kernel", "kernel_ms": round(bp_ms, 3), "peak_source": peak_src,
+                     "traffic": measured_traffic(total_iters), "kernel": "flood_i8_kernel", "kernel_ms": round(bp_ms, 3), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg},
         "e2e": {"value": round(e2e_gbps, 4), "unit": "Gbit/s", "h2d_bytes_per_step": e2e_frames * N * 4,
                 "d2h_bytes_per_step": e2e_frames * (K_INFO + 4), "frames_per_step": e2e_frames, "info_bit_errors": bit_errors},

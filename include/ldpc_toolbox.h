@@ -115,6 +115,13 @@ int64_t ldpc_toolbox_decoder_last_timing(void *decoder, float *ms3);
 void *ldpc_toolbox_ber_ctor(const char *alist, int alist_is_path, const char *implementation,
                             const char *puncturing, int device, int max_tiles);
 void ldpc_toolbox_ber_dtor(void *ber);
+/* Modulation of the simulated link: "BPSK" (default) or "8PSK" (reference src/simulation/factory.rs:56-86,
+ * src/simulation/modulation.rs:144-288: DVB-S2 Gray mapping, complex AWGN, exact max* demapper), and the
+ * DVB-S2 bit interleaver (reference src/simulation/interleaving.rs:40-85, src/simulation/ber.rs:250-252):
+ * interleaving_columns = 0 none, n > 0 n columns, n < 0 |n| columns with rows read backwards.
+ * Returns 0, or -2 (unknown name; frame length not a multiple of 3 bits / of the columns — the
+ * reference panics on those at the first frame). */
+int32_t ldpc_toolbox_ber_set_modulation(void *ber, const char *modulation, int32_t interleaving_columns);
 int32_t ldpc_toolbox_ber_run(void *ber, float ebn0_db, uint32_t max_iterations,
                              uint64_t first_frame, uint64_t nframes, uint64_t seed,
                              uint64_t bch_max_errors, uint64_t *counters);

@@ -4,7 +4,7 @@ Host-side mirror of the reference's simulation layer:
   BerTestParameters / BerTest.new      reference src/simulation/ber.rs:96-158, :246-282
   BerTest.run / do_run (stop rule)     reference src/simulation/ber.rs:288-368, :522-531
   Statistics / CodeStatistics          reference src/simulation/ber.rs:160-195, :551-581
-  Modulation names                     reference src/simulation/factory.rs:56-86 (BPSK only here)
+  Modulation names                     reference src/simulation/factory.rs:56-86 (BPSK, 8PSK)
 
 The per-frame work (random message, encode, puncture, BPSK, AWGN, decode, error counting) runs on
 the GPU; this module only shards global frame indices over GPUs / ranks, sums nine counters and
@@ -30,13 +30,19 @@ NUM_COUNTERS = len(COUNTER_NAMES)
 class BerEngine:
     """One GPU's engine: simulate a range of global frame indices at one Eb/N0, add to counters."""
 
-    def __init__(self, alist: str, implementation: str = "Phif64", puncturing: str = "", device: int = -1, max_tiles: int = 0):
+    def __init__(self, alist: str, implementation: str = "Phif64", puncturing: str = "", device: int = -1, max_tiles: int = 0,
+                 modulation: str = "BPSK", interleaving: Optional[int] = None):
         import os
         self._lib = capi.load()
         is_path = int("\n" not in alist and os.path.exists(alist))
         self._h = self._lib.ldpc_toolbox_ber_ctor(alist.encode(), is_path, implementation.encode(), puncturing.encode(), device, max_tiles)
         if not self._h:
             raise ValueError(f"ldpc_toolbox_ber_ctor returned NULL: {capi.last_error()}")
+        if modulation != "BPSK" or interleaving:
+            if self._lib.ldpc_toolbox_ber_set_modulation(self._h, modulation.encode(), int(interleaving or 0)) != 0:
+                err = capi.last_error()
+                self.close()
+                raise ValueError(f"ldpc_toolbox_ber_set_modulation: {err}")
         dims = (C.c_uint64 * 3)()
         self._lib.ldpc_toolbox_ber_dims(self._h, dims)
         self.k, self.n_cw, self.n = int(dims[0]), int(dims[1]), int(dims[2])

@@ -35,6 +35,7 @@ _SIGS = {
     "ldpc_toolbox_decoder_last_timing": (C.c_int64, [C.c_void_p, C.c_void_p]),
     "ldpc_toolbox_ber_ctor": (C.c_void_p, [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int]),
     "ldpc_toolbox_ber_dtor": (None, [C.c_void_p]),
+    "ldpc_toolbox_ber_set_modulation": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int32]),
     "ldpc_toolbox_ber_run": (C.c_int32, [C.c_void_p, C.c_float, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "ldpc_toolbox_ber_run_dump": (C.c_int32, [C.c_void_p, C.c_float, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -5,7 +5,7 @@
 
 Same flags, banner and result table as the reference; additions: --gpus, --batch,
 --seed, --max-frames.  `--num-threads` is accepted and reported but the work runs on GPUs.
-Modulation: BPSK (8PSK + interleaving is a "next" row).
+Modulation: BPSK or 8PSK, with the DVB-S2 bit interleaver (--interleaving n, negative = rows backwards).
 """
 from __future__ import annotations
 
@@ -143,9 +143,8 @@ def build_parser() -> argparse.ArgumentParser:
 
 
 def run_ber(a, out=sys.stdout) -> list[Statistics]:
-    if a.modulation != "BPSK" or a.interleaving is not None:
-        raise SystemExit("only BPSK without interleaving runs on the GPU engine (8PSK + interleaver: next row, SURVEY.md §8f-2)")
-    engines = [BerEngine(a.alist, a.decoder, a.puncturing or "", device=g) for g in range(a.gpus)]
+    engines = [BerEngine(a.alist, a.decoder, a.puncturing or "", device=g, modulation=a.modulation, interleaving=a.interleaving)
+               for g in range(a.gpus)]
     e0 = engines[0]
     if a.batch <= 0:
         # aim at ~2 resident 512-frame tiles per SM for big codes, fewer frames for small ones

@@ -52,6 +52,9 @@ struct FrontendParams {
     uint64_t first_frame;       // global index of frame 0 of this launch
     uint32_t seed_lo, seed_hi;
     float sigma, llr_scale;     // llr = llr_scale * y, llr_scale = -2/sigma^2
+    int modulation;             // 0: BPSK, 1: 8PSK (DVB-S2 Gray mapping)
+    int il_cols, il_backwards;  // bit interleaver: columns (0 = none), rows read backwards
+    double sigma_d;             // 8PSK: noise sigma in f64 (demapper scale 1/sigma^2)
     float* llrs;                // [nframes][n_tx]
     uint32_t* messages;         // [nframes][ceil(k/32)]
 };
@@ -161,8 +164,46 @@ __global__ void __launch_bounds__(256) ber_frontend_kernel(FrontendParams p) {
         __syncthreads();
     }
 
-    // ---- puncture, BPSK, AWGN, demodulate: four transmitted symbols per thread and Philox call
     float* out = p.llrs + (size_t)blockIdx.x * p.n_tx;
+    auto tx_bit = [&](int t) -> uint32_t {                       // t-th transmitted (punctured) code bit
+        const int v = p.kept ? __ldg(p.kept + t) : t;
+        return v < p.k ? (msg[v >> 5] >> (v & 31)) & 1u : (par[(v - p.k) >> 5] >> ((v - p.k) & 31)) & 1u;
+    };
+    if (p.modulation == 1) {
+        // ---- 8PSK: interleave (interleaving.rs:40-58), map (modulation.rs:166-178), complex AWGN
+        // (channel.rs:74-81), exact max* demapper (modulation.rs:222-262), deinterleave (:64-85).
+        // One symbol per thread; the LLR of interleaved position i goes back to transmitted position t(i).
+        const int nsym = p.n_tx / 3, rows = p.il_cols > 0 ? p.n_tx / p.il_cols : 0;
+        auto src_of = [&](int i) {                               // transmitted index read at interleaved position i
+            if (p.il_cols <= 0) return i;
+            const int r = i / p.il_cols, c = i % p.il_cols;
+            return (p.il_backwards ? p.il_cols - 1 - c : c) * rows + r;
+        };
+        const double a = 0.70710678118654757, scale = 1.0 / (p.sigma_d * p.sigma_d);
+        auto maxstar = [](double x, double y) { return fmax(x, y) + log1p(exp(-fabs(x - y))); };
+        for (int sidx = threadIdx.x; sidx < nsym; sidx += blockDim.x) {
+            const int t0 = src_of(3 * sidx), t1 = src_of(3 * sidx + 1), t2 = src_of(3 * sidx + 2);
+            const uint32_t b0 = tx_bit(t0), b1 = tx_bit(t1), b2 = tx_bit(t2);
+            // (b0, b1, b2) -> point; index = b0 | b1 << 1 | b2 << 2
+            const double re_tab[8] = {a, 0.0, -1.0, -a, 1.0, a, -a, 0.0};      // 000 100 010 110 001 101 011 111
+            const double im_tab[8] = {a, 1.0, 0.0, a, 0.0, -a, -a, -1.0};
+            const int idx = (int)(b0 | b1 << 1 | b2 << 2);
+            uint4 r = rng(f_lo, f_hi, (uint32_t)sidx, kStreamNoise);
+            const double rad = sqrt(-2.0 * log(((double)r.x + 0.5) * 2.3283064365386963e-10));
+            double sn, cs;
+            sincospi(2.0 * ((double)r.y + 0.5) * 2.3283064365386963e-10, &sn, &cs);
+            const double yr = (re_tab[idx] + p.sigma_d * rad * cs) * scale, yi = (im_tab[idx] + p.sigma_d * rad * sn) * scale;
+            const double d000 = yr * a + yi * a, d100 = yi, d110 = -yr * a + yi * a, d010 = -yr, d011 = -yr * a - yi * a, d111 = -yi,
+                         d101 = yr * a - yi * a, d001 = yr;
+            const double l0 = maxstar(maxstar(maxstar(d000, d001), d010), d011) - maxstar(maxstar(maxstar(d100, d101), d110), d111);
+            const double l1 = maxstar(maxstar(maxstar(d000, d001), d100), d101) - maxstar(maxstar(maxstar(d010, d011), d110), d111);
+            const double l2 = maxstar(maxstar(maxstar(d000, d010), d100), d110) - maxstar(maxstar(maxstar(d001, d011), d101), d111);
+            out[t0] = (float)l0; out[t1] = (float)l1; out[t2] = (float)l2;
+        }
+        return;
+    }
+    // ---- puncture, BPSK, AWGN, demodulate: four transmitted symbols per thread and Philox call
+    // (a bit interleaver in front of BPSK only renames i.i.d. noise samples, so it is the identity here)
     for (int t4 = threadIdx.x; t4 * 4 < p.n_tx; t4 += blockDim.x) {
         uint4 r = rng(f_lo, f_hi, (uint32_t)t4, kStreamNoise);
         // Box-Muller on (u1, u2) pairs; u1 in (0,1] with full 32-bit resolution, log in f64
@@ -179,8 +220,7 @@ __global__ void __launch_bounds__(256) ber_frontend_kernel(FrontendParams p) {
         for (int i = 0; i < 4; ++i) {
             int t = t4 * 4 + i;
             if (t >= p.n_tx) break;
-            int v = p.kept ? __ldg(p.kept + t) : t;
-            uint32_t bit = v < p.k ? (msg[v >> 5] >> (v & 31)) & 1u : (par[(v - p.k) >> 5] >> ((v - p.k) & 31)) & 1u;
+            uint32_t bit = tx_bit(t);
             float y = (bit ? 1.0f : -1.0f) + p.sigma * z[i];
             out[t] = p.llr_scale * y;
         }
@@ -281,10 +321,23 @@ std::unique_ptr<BerEngine> BerEngine::create(const Graph& g, const DecoderImplem
     return e;
 }
 
-double BerEngine::noise_sigma(float ebn0_db) const {   // ber.rs:300-302, BPSK: 1 bit per symbol
+double BerEngine::noise_sigma(float ebn0_db) const {   // ber.rs:300-302; BITS_PER_SYMBOL modulation.rs:74, :151
     const double ebn0 = pow(10.0, 0.1 * (double)ebn0_db);
-    const double esn0 = rate_ * 1.0 * ebn0;
+    const double esn0 = rate_ * (modulation_ == 1 ? 3.0 : 1.0) * ebn0;
     return sqrt(0.5 / esn0);
+}
+
+bool BerEngine::set_modulation(const std::string& name, int interleaving_columns) {
+    int mod;
+    if (name == "BPSK") mod = 0;                        // names: src/simulation/factory.rs:56-86
+    else if (name == "8PSK") mod = 1;
+    else { set_last_error("invalid modulation"); return false; }
+    const int cols = interleaving_columns < 0 ? -interleaving_columns : interleaving_columns;
+    // the reference panics on these at the first frame (modulation.rs:195, interleaving.rs:45)
+    if (mod == 1 && n_tx_ % 3 != 0) { set_last_error("8PSK needs a frame length that is a multiple of 3 bits"); return false; }
+    if (cols > 0 && n_tx_ % cols != 0) { set_last_error("frame length not divisible by the interleaver columns"); return false; }
+    modulation_ = mod; il_cols_ = cols; il_backwards_ = interleaving_columns < 0 ? 1 : 0;
+    return true;
 }
 
 bool BerEngine::ensure(size_t nframes) {
@@ -321,6 +374,7 @@ bool BerEngine::run(float ebn0_db, uint32_t max_iterations, uint64_t first_frame
     memcpy(&eb_bits, &ebn0_db, 4);
     fp.seed_lo = (uint32_t)seed; fp.seed_hi = (uint32_t)(seed >> 32) ^ eb_bits;
     fp.sigma = (float)sigma; fp.llr_scale = (float)(-2.0 / (sigma * sigma));
+    fp.modulation = modulation_; fp.il_cols = il_cols_; fp.il_backwards = il_backwards_; fp.sigma_d = sigma;
     fp.llrs = d_llrs_; fp.messages = d_messages_;
     const size_t smem = ((size_t)(k_ + 31) / 32 + (size_t)(m_ + 31) / 32 + 4) * sizeof(uint32_t);
     if (smem > 48 * 1024) LDPC_CUDA_CHECK(cudaFuncSetAttribute(ber_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -6,6 +6,7 @@
 
 #include <cstdint>
 #include <memory>
+#include <string>
 
 #include "decoder.hpp"
 #include "host.hpp"
@@ -28,6 +29,9 @@ public:
              uint64_t bch_max_errors, uint64_t* counters, float* dump_llrs = nullptr, uint8_t* dump_decoded = nullptr,
              int32_t* dump_iters = nullptr, uint32_t* dump_messages = nullptr);
     double noise_sigma(float ebn0_db) const;
+    // "BPSK" or "8PSK" (reference src/simulation/factory.rs:56-86); interleaving_columns: 0 = none, n = DVB-S2
+    // bit interleaver with n columns, -n = rows read backwards (reference src/simulation/ber.rs:250-252)
+    bool set_modulation(const std::string& name, int interleaving_columns);
     int n() const { return n_; }
     int k() const { return k_; }
     int n_tx() const { return n_tx_; }       // transmitted symbols per frame ("Frame size (N)")
@@ -41,6 +45,7 @@ private:
     EncoderPlan plan_;
     std::unique_ptr<LdpcDecoder> decoder_;
     int n_ = 0, m_ = 0, k_ = 0, n_tx_ = 0, device_ = 0, g0_words_ = 0;
+    int modulation_ = 0, il_cols_ = 0, il_backwards_ = 0;
     double rate_ = 0;
     int* d_h0_ptr_ = nullptr; int* d_h0_idx_ = nullptr; uint32_t* d_g0_ = nullptr; int* d_kept_ = nullptr;
     float* d_llrs_ = nullptr; uint32_t* d_messages_ = nullptr; uint8_t* d_decoded_ = nullptr; int32_t* d_iters_ = nullptr;

@@ -238,6 +238,11 @@ void* ldpc_toolbox_ber_ctor(const char* alist, int alist_is_path, const char* im
 
 void ldpc_toolbox_ber_dtor(void* ber) { delete static_cast<BerEngine*>(ber); }
 
+int32_t ldpc_toolbox_ber_set_modulation(void* ber, const char* modulation, int32_t interleaving_columns) {
+    if (!ber || !modulation) return -2;
+    return static_cast<BerEngine*>(ber)->set_modulation(modulation, interleaving_columns) ? 0 : -2;
+}
+
 int32_t ldpc_toolbox_ber_run(void* ber, float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes, uint64_t seed,
                              uint64_t bch_max_errors, uint64_t* counters) {
     if (!ber || !counters) return -2;

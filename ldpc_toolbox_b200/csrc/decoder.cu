@@ -329,7 +329,7 @@ private:
         }
         if (off > 0x7fffffffu) { set_last_error("level schedule too large"); return false; }
         ell_size_ = std::max<size_t>(off, 1);
-        smem_threads_ = std::min(512, std::max(64, (widest + 31) / 32 * 32));
+        smem_threads_ = std::min(256, std::max(64, (widest + 31) / 32 * 32));      // layered_smem_impl.cuh: at most 256
         if (!d_row_base_.upload(row_base) || !d_row_stride_.upload(row_stride) || !d_row_deg_.upload(row_deg) || !d_ell_col_.upload(ell_col))
             return false;
         sg_.n = g_.n; sg_.m = g_.m; sg_.num_levels = num_levels_; sg_.level_ptr = d_level_ptr_.p; sg_.row_base = d_row_base_.p;

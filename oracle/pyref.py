@@ -433,3 +433,74 @@ def decode(h: SparseMatrix, name: str, llrs, max_iterations: int):
         if _check_llrs(h, out, A.hard):
             return [int(A.hard(x)) for x in out], it, True, out
     return [int(A.hard(x)) for x in out], max_iterations, False, out
+
+
+# ---------------------------------------------------------------------------------------------
+# 8PSK + bit interleaver (test infrastructure, like everything in oracle/)
+# ---------------------------------------------------------------------------------------------
+def interleave(x, columns: int, backwards: bool = False):
+    """reference src/simulation/interleaving.rs:40-58: write the codeword by rows into a
+    (columns x len/columns) matrix, read it by columns (rows of the transpose optionally reversed)."""
+    import numpy as np
+    x = np.asarray(x)
+    assert x.size % columns == 0
+    t = x.reshape(columns, x.size // columns).T
+    if backwards:
+        t = t[:, ::-1]
+    return np.ascontiguousarray(t).reshape(-1)
+
+
+def deinterleave(x, columns: int, backwards: bool = False):
+    """reference src/simulation/interleaving.rs:64-85"""
+    import numpy as np
+    x = np.asarray(x)
+    assert x.size % columns == 0
+    t = x.reshape(x.size // columns, columns).T
+    if backwards:
+        t = t[::-1, :]
+    return np.ascontiguousarray(t).reshape(-1)
+
+
+_PSK8 = None
+
+
+def _psk8_points():
+    global _PSK8
+    if _PSK8 is None:
+        a = math.sqrt(0.5)
+        # reference src/simulation/modulation.rs:166-178, keyed by (b0, b1, b2)
+        _PSK8 = {(0, 0, 0): complex(a, a), (1, 0, 0): complex(0, 1), (1, 1, 0): complex(-a, a), (0, 1, 0): complex(-1, 0),
+                 (0, 1, 1): complex(-a, -a), (1, 1, 1): complex(0, -1), (1, 0, 1): complex(a, -a), (0, 0, 1): complex(1, 0)}
+    return _PSK8
+
+
+def psk8_modulate(bits):
+    """reference src/simulation/modulation.rs:189-203"""
+    bits = [int(b) for b in bits]
+    assert len(bits) % 3 == 0
+    pts = _psk8_points()
+    return [pts[(bits[i], bits[i + 1], bits[i + 2])] for i in range(0, len(bits), 3)]
+
+
+def _maxstar(a, b):
+    return max(a, b) + math.log1p(math.exp(-abs(a - b)))
+
+
+def psk8_demodulate(symbols, noise_sigma: float):
+    """reference src/simulation/modulation.rs:222-262: exact LLRs with max*, reduce order as written there"""
+    pts = _psk8_points()
+    scale = 1.0 / (noise_sigma * noise_sigma)
+    out = []
+    for s in symbols:
+        s = s * scale
+        d = {k: s.real * p.real + s.imag * p.imag for k, p in pts.items()}
+
+        def red(keys):
+            acc = d[keys[0]]
+            for k in keys[1:]:
+                acc = _maxstar(acc, d[k])
+            return acc
+        out.append(red([(0, 0, 0), (0, 0, 1), (0, 1, 0), (0, 1, 1)]) - red([(1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 1, 1)]))
+        out.append(red([(0, 0, 0), (0, 0, 1), (1, 0, 0), (1, 0, 1)]) - red([(0, 1, 0), (0, 1, 1), (1, 1, 0), (1, 1, 1)]))
+        out.append(red([(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0)]) - red([(0, 0, 1), (0, 1, 1), (1, 0, 1), (1, 1, 1)]))
+    return out

@@ -109,3 +109,46 @@ def test_cli_ber_output(tmp_path, capsys):
     rows = [l for l in out.read_text().split("\n") if l.startswith("   0.")]
     assert len(rows) == 2 and rows[0].startswith("   0.50 |") and rows[1].startswith("   0.75 |")
     assert rows[0].count("|") == 10
+
+
+@pytest.mark.parametrize("interleaving", [None, 3, -3])
+def test_psk8_link_noiseless_limit(oracle, interleaving):
+    """8PSK + DVB-S2 bit interleaver on the device (reference modulation.rs:144-288, interleaving.rs:40-85):
+    at a very high Eb/N0 the dumped LLRs must be the max* demapping of the noiseless symbols of the
+    interleaved codeword, put back in codeword order."""
+    import pyref
+    alist = codes.alist_for("dvbs2:R1_2short")
+    eng = BerEngine(alist, "Minstarapproxi8", modulation="8PSK", interleaving=interleaving)
+    ebn0 = 50.0
+    counters, llrs, dec, its, msg = eng.run_dump(ebn0, 5, first_frame=7, nframes=6)
+    sigma = eng.noise_sigma(ebn0)
+    # Es/N0 uses 3 bits per symbol (ber.rs:300-302, modulation.rs:151)
+    assert abs(sigma - oracle.lib.ldpc_oracle_noise_sigma(eng.rate, 3.0, ebn0)) < 1e-12
+    enc = oracle.encoder(alist)
+    cols, back = (abs(interleaving), interleaving < 0) if interleaving else (0, False)
+    for f in range(msg.shape[0]):
+        cw = enc.encode(msg[f], eng.n)
+        tx = pyref.interleave(cw, cols, back) if cols else cw
+        ref = np.array(pyref.psk8_demodulate(pyref.psk8_modulate(tx), sigma))
+        ref = pyref.deinterleave(ref, cols, back) if cols else ref
+        assert ((llrs[f] <= 0) == (cw == 1)).all()
+        assert np.allclose(llrs[f], ref, rtol=0.05, atol=0.0)          # noise of sigma = 0.002 on unit symbols
+    assert counters["bit_errors"] == 0 and (dec == msg).all()
+
+
+def test_psk8_waterfall_sits_above_bpsk():
+    """Same code and decoder: 8PSK needs more Eb/N0 than BPSK, and decodes cleanly once it has it."""
+    alist = codes.alist_for("dvbs2:R1_2short")
+    bpsk = BerEngine(alist, "Minstarapproxi8")
+    psk8 = BerEngine(alist, "Minstarapproxi8", modulation="8PSK", interleaving=3)
+    fer = lambda eng, e: (lambda c: c[2] / c[0])(eng.run(e, 30, 0, 512))
+    assert fer(bpsk, 1.6) < 0.05
+    assert fer(psk8, 1.6) > 0.5
+    assert fer(psk8, 4.5) < 0.05
+
+
+def test_psk8_rejects_bad_lengths():
+    with pytest.raises(ValueError):
+        BerEngine(codes.alist_for("ar4ja:1/2:1024"), "Phif64", modulation="8PSK")       # 2560 bits: not a multiple of 3
+    with pytest.raises(ValueError):
+        BerEngine(codes.alist_for("dvbs2:R1_2short"), "Phif64", modulation="QPSK")

@@ -139,3 +139,23 @@ def test_implementation_names(oracle):
     assert sum(n.startswith("HL") for n in names) == 12
     with pytest.raises(ValueError):
         oracle.decoder(JOHNSON, "phif64")      # case-sensitive
+
+
+# ---- src/simulation/interleaving.rs:92-125 and src/simulation/modulation.rs:311-349 (8PSK) -------
+def test_interleaver_kats():
+    import pyref
+    assert pyref.interleave([0, 1, 2, 3, 4, 5], 3).tolist() == [0, 2, 4, 1, 3, 5]
+    assert pyref.interleave([0, 1, 2, 3, 4, 5], 3, True).tolist() == [4, 2, 0, 5, 3, 1]
+    for back in (False, True):
+        x = np.arange(24)
+        assert pyref.deinterleave(pyref.interleave(x, 3, back), 3, back).tolist() == x.tolist()
+
+
+def test_psk8_kats():
+    import pyref
+    a = np.sqrt(0.5)
+    x = pyref.psk8_modulate([1, 1, 0, 0, 0, 0, 1, 0, 1])
+    assert np.allclose(x, [complex(-a, a), complex(a, a), complex(a, -a)], atol=0, rtol=0)
+    llr = pyref.psk8_demodulate([complex(1, 0), complex(a, a), complex(0, 1)], 1.0)
+    signs = [v > 0 for v in llr]
+    assert signs == [True, True, False, True, True, True, False, True, True]      # 001, 000, 100
