@@ -1,4 +1,6 @@
-"""`ber` command line, drop-in for `ldpc-toolbox ber` (reference src/cli/ber.rs:39-341).
+"""Command line: `ber` is a drop-in for `ldpc-toolbox ber` (reference src/cli/ber.rs:39-341); `encode`,
+`systematic`, `dvbs2`, `nr5g` and `ccsds` mirror the reference's subcommands that sit either side of the
+hot path (src/cli/encode.rs, systematic.rs, dvbs2.rs, nr5g.rs, ccsds.rs; `--girth` is out of scope).
 
     python -m ldpc_toolbox_b200.cli ber <alist> --min-ebn0 0.5 --max-ebn0 1.5 --step-ebn0 0.25 \
         --decoder Minstarapproxi8 --max-iter 25 [--gpus 8] [--batch 75776] [--seed 24301]
@@ -139,7 +141,114 @@ def build_parser() -> argparse.ArgumentParser:
     b.add_argument("--batch", type=int, default=0, help="frames per GPU per launch (default: by code size)")
     b.add_argument("--seed", type=int, default=0x5EED)
     b.add_argument("--max-frames", type=int, help="stop an Eb/N0 point after this many frames")
+    e = sub.add_parser("encode", help="Performs LDPC encoding")                       # reference src/cli/encode.rs:19-32
+    e.add_argument("alist", help="alist file for the code")
+    e.add_argument("input", help="input file (information words as unpacked bits)")
+    e.add_argument("output", help="output file (punctured words as unpacked bits)")
+    e.add_argument("--puncturing")
+    sy = sub.add_parser("systematic", help="Converts a parity check matrix into systematic form")   # src/cli/systematic.rs
+    sy.add_argument("alist", help="alist file for the code")
+    d = sub.add_parser("dvbs2", help="Generates the alist of DVB-S2 LDPCs")           # reference src/cli/dvbs2.rs:12-24
+    d.add_argument("-r", "--rate", required=True)
+    d.add_argument("--short", action="store_true")
+    d.add_argument("--girth", action="store_true")
+    n = sub.add_parser("nr5g", help="Generates the alist of 5G NR LDPCs")             # reference src/cli/nr5g.rs:8-19
+    n.add_argument("--base-graph", type=int, required=True, choices=[1, 2])
+    n.add_argument("--lifting-size", type=int, required=True)
+    n.add_argument("--girth", action="store_true")
+    c = sub.add_parser("ccsds", help="Generates the alist of CCSDS LDPCs")            # reference src/cli/ccsds.rs:10-22
+    c.add_argument("-r", "--rate", required=True)
+    c.add_argument("--block-size", type=int, required=True)
+    c.add_argument("--girth", action="store_true")
     return ap
+
+
+def run_encode(a) -> None:
+    """reference src/cli/encode.rs:34-70: k unpacked bits in, n bytes out per word (the punctured word, then the
+    rest of the n-byte buffer, which the reference never writes and so stays zero); a trailing partial word is dropped."""
+    import numpy as np
+
+    from .decoder import Encoder
+    text = open(a.alist).read()
+    first = text.split("\n", 1)[0].split()
+    ncols, nrows = int(first[0]), int(first[1])
+    k = ncols - nrows
+    enc = Encoder(a.alist, a.puncturing or "")
+    out_len = ncols
+    if a.puncturing:
+        pat = [int(x) for x in a.puncturing.split(",")]
+        out_len = ncols // len(pat) * sum(pat)
+    with open(a.input, "rb") as fi, open(a.output, "wb") as fo:
+        while True:
+            word = fi.read(k)
+            if len(word) < k or k == 0:
+                break
+            cw = enc.encode(np.frombuffer(word, dtype=np.uint8), out_len)
+            buf = np.zeros(ncols, dtype=np.uint8)
+            buf[:out_len] = cw
+            fo.write(buf.tobytes())
+
+
+def parity_to_systematic(alist_text: str) -> str:
+    """reference src/systematic.rs:40-93: permute the columns so that the last n-k columns (the first
+    linearly independent ones, in order) are invertible; the others keep their order in front."""
+    import numpy as np
+
+    from . import codes
+    lines = alist_text.split("\n")
+    ncols, nrows = (int(x) for x in lines[0].split())
+    if nrows > ncols:
+        raise SystemExit("the parity check matrix has more rows than columns")
+    cols = [[int(x) - 1 for x in lines[4 + c].split() if int(x) > 0] for c in range(ncols)]      # sparse.rs:372-386
+    words = (ncols + 63) // 64
+    a = np.zeros((nrows, words), dtype=np.uint64)
+    for c, rows in enumerate(cols):
+        for r in rows:
+            a[r, c >> 6] ^= np.uint64(1) << np.uint64(c & 63)
+    pivots, krow = [], 0
+    for j in range(ncols):                               # linalg.rs:68-104 (row echelon form over GF(2))
+        if krow >= nrows:
+            break
+        bit = (a[krow:, j >> 6] >> np.uint64(j & 63)) & np.uint64(1)
+        nz = np.flatnonzero(bit)
+        if nz.size == 0:
+            continue
+        s = krow + int(nz[0])
+        if s != krow:
+            a[[s, krow]] = a[[krow, s]]
+        below = krow + 1 + np.flatnonzero((a[krow + 1:, j >> 6] >> np.uint64(j & 63)) & np.uint64(1))
+        a[below] ^= a[krow]
+        pivots.append(j)
+        krow += 1
+    if len(pivots) < nrows:
+        raise SystemExit("the parity check matrix does not have full rank")
+    piv = set(pivots)
+    order = [c for c in range(ncols) if c not in piv] + pivots
+    r = np.array([row for c in order for row in cols[c]], dtype=np.int64)
+    cc = np.array([i for i, c in enumerate(order) for _ in cols[c]], dtype=np.int64)
+    return codes.alist_text(codes.Edges(nrows, ncols, r, cc).finalize())
+
+
+DVBS2_RATES = ("1/4", "1/3", "2/5", "1/2", "3/5", "2/3", "3/4", "4/5", "5/6", "8/9", "9/10")
+
+
+def run_codes(a, out=None) -> None:
+    from . import codes
+    out = out or sys.stdout
+    if a.girth:
+        raise SystemExit("--girth belongs to the code-design tools, which are outside this framework's scope (DESIGN.md section 1)")
+    if a.command == "dvbs2":
+        if a.rate not in DVBS2_RATES or (a.short and a.rate == "9/10"):                  # cli/dvbs2.rs:27-58
+            raise SystemExit(f"Invalid rate {a.rate} for {'short' if a.short else 'normal'} FECFRAME")
+        out.write(codes.alist_for("dvbs2:R" + a.rate.replace("/", "_") + ("short" if a.short else "")))
+    elif a.command == "nr5g":
+        out.write(codes.alist_for(f"nr5g:{a.base_graph}:{a.lifting_size}") + "\n")       # cli/nr5g.rs:33 uses println!
+    else:
+        if a.rate not in ("1/2", "2/3", "4/5"):
+            raise SystemExit(f"Invalid code rate {a.rate}")
+        if a.block_size not in (1024, 4096, 16384):
+            raise SystemExit(f"Invalid information block size k = {a.block_size}")
+        out.write(codes.alist_for(f"ar4ja:{a.rate}:{a.block_size}"))
 
 
 def run_ber(a, out=sys.stdout) -> list[Statistics]:
@@ -195,6 +304,12 @@ def main(argv=None) -> int:
     a = build_parser().parse_args(argv)
     if a.command == "ber":
         run_ber(a)
+    elif a.command == "encode":
+        run_encode(a)
+    elif a.command == "systematic":
+        sys.stdout.write(parity_to_systematic(open(a.alist).read()) + "\n")             # cli/systematic.rs:23 uses println!
+    else:
+        run_codes(a)
     return 0
 
 

@@ -182,3 +182,43 @@ def test_ber_driver_world_size_2_gloo():
     from ldpc_toolbox_b200.ber import BerTest
     single = BerTest([FakeEngine(), FakeEngine()], k=10, ebn0s_db=[1.0], max_iterations=5, max_frame_errors=30, batch=64).run()[0]
     assert (frames, fe, be, iters) == (single.num_frames, single.ldpc.frame_errors, single.ldpc.bit_errors, single.total_iterations)
+
+
+def test_systematic_reference_kat():
+    """reference src/systematic.rs:99-121 (to_systematic), through alist text."""
+    from ldpc_toolbox_b200 import cli, codes
+
+    def alist(ncols, nrows, colmap):
+        r = [row for c, rows in colmap.items() for row in rows]
+        c = [c for c, rows in colmap.items() for _ in rows]
+        return codes.alist_text(codes.Edges(nrows, ncols, np.array(r), np.array(c)).finalize())
+
+    h = alist(9, 3, {0: [0, 1, 2], 1: [0, 2], 3: [1], 4: [0, 1], 5: [1, 2], 6: [0, 2], 7: [1], 8: [0, 2]})
+    expected = alist(9, 3, {6: [0, 1, 2], 7: [0, 2], 1: [1], 8: [0, 1], 2: [1, 2], 3: [0, 2], 4: [1], 5: [0, 2]})
+    assert cli.parity_to_systematic(h) == expected
+    rank_deficient = alist(4, 2, {0: [0, 1], 1: [0, 1]})
+    with pytest.raises(SystemExit):
+        cli.parity_to_systematic(rank_deficient)
+
+
+def test_cli_encode_and_code_generators(tmp_path, oracle, capsys):
+    from ldpc_toolbox_b200 import cli, codes
+    alist = tmp_path / "c.alist"
+    assert cli.main(["ccsds", "--rate", "1/2", "--block-size", "1024"]) == 0
+    text = capsys.readouterr().out
+    assert text == codes.alist_for("ar4ja:1/2:1024")
+    alist.write_text(text)
+    assert cli.main(["dvbs2", "--rate", "1/2", "--short"]) == 0
+    assert capsys.readouterr().out == codes.alist_for("dvbs2:R1_2short")
+    assert cli.main(["nr5g", "--base-graph", "2", "--lifting-size", "24"]) == 0
+    assert capsys.readouterr().out == codes.alist_for("nr5g:2:24") + "\n"
+    with pytest.raises(SystemExit):
+        cli.main(["dvbs2", "--rate", "9/10", "--short"])
+    rng = np.random.default_rng(5)
+    msgs = rng.integers(0, 2, size=(3, 1024), dtype=np.uint8)
+    (tmp_path / "in.u8").write_bytes(msgs.tobytes() + b"\x01\x00\x01")           # trailing partial word is dropped
+    assert cli.main(["encode", str(alist), str(tmp_path / "in.u8"), str(tmp_path / "out.u8"), "--puncturing", "1,1,1,1,0"]) == 0
+    out = np.frombuffer((tmp_path / "out.u8").read_bytes(), dtype=np.uint8).reshape(3, 2560)
+    enc = oracle.encoder(text, "1,1,1,1,0")
+    for m, o in zip(msgs, out):
+        assert (o[:2048] == enc.encode(m, 2048)).all() and not o[2048:].any()
