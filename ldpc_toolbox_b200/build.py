@@ -66,10 +66,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     log = []
     # the image exports CXX=/opt/gcc/bin/g++ (a wrapper); nvcc must use the system host compiler
     ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+    names, headers = _sources()
+    hh = hashlib.sha256()
+    for f in headers:
+        hh.update(open(os.path.join(CSRC, f), "rb").read())
+    hh.update(open(os.path.join(HERE, "..", "include", "ldpc_toolbox.h"), "rb").read())
+    hh.update(" ".join(NVCC_FLAGS).encode())
+    header_digest = hh.hexdigest()
+
     def compile_one(src):
+        # per translation unit: recompiled only when its own source, a header or the flags changed
         obj = os.path.join(OUT_DIR, src.rsplit(".", 1)[0] + ".o")
+        tu = hashlib.sha256(open(os.path.join(CSRC, src), "rb").read() + header_digest.encode()).hexdigest()
+        tu_stamp = obj + ".stamp"
+        if not force and os.path.exists(obj) and os.path.exists(tu_stamp) and open(tu_stamp).read() == tu:
+            return obj, f"# {src}: up to date\n", 0
         cmd = [nvcc] + ccbin + NVCC_FLAGS + ["-x", "cu" if src.endswith(".cu") else "c++", "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode == 0:
+            open(tu_stamp, "w").write(tu)
         return obj, "$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr, r.returncode
 
     from concurrent.futures import ThreadPoolExecutor

@@ -23,18 +23,21 @@
 // Exactness notes: the min* fold g(a,b)=max(0,min(a,b)-T[|a-b|]) is not
 // associative, so for every excluded edge j the others are folded left-to-right in row order;
 // the only sharing is the common prefix fold(x_0..x_{j-1}).  With d = a - acc,
-//      g(a, acc) = max(0, acc + U[d]),   U[d] = min(d, 0) - T[|d|]
-// so one fold step is: subtract, one table read, one fused add-max(0) (VIADDMNMX.RELU).
-// U is a 255-entry int8 table in shared memory.
+//      g(a, acc) = max(0, acc + U[d]),   U[d] = min(d, 0) - T[|d|].
+// The unrolled path carries a chain as the index of its next table read, idx = a_next - acc: the
+// table returns V[idx] = idx - U[idx] and the following index is min(V[idx] + (a' - a), a'), so a
+// fold step is one LDS.U8 and one VIADDMNMX (check_word).  U, V and T are small tables in shared
+// memory (the A-Min* variants and the generic-degree path use U and T directly).
 //
 // Storage format: every int8 quantity in HBM (messages, channel LLRs) is kept in offset binary,
 // byte = value + 128 in [1, 255].  |v| of four frames is then ONE instruction (VABSDIFF4.U8 against
 // 0x80808080), the variable node's carry-free SWAR sums need no re-biasing, and signs travel in bit 7.
 //
-// Pipe balance: the kernel is bound by the integer ALU pipe (min/max, LOP3, PRMT, VIADDMNMX), while
-// the FMA pipe (IMAD) idles.  Plain adds/subtracts/shifts-and-ors on the critical path are therefore
-// written as mad.lo with a multiplier taken from a kernel parameter (ptxas cannot fold it), which
-// pins them to the FMA pipe: a fold step is IMAD + LDS + VIADDMNMX = one instruction per pipe.
+// Pipe balance: the check pass is bound by the table reads (one shared-memory wavefront per warp
+// read) together with the half-rate integer pipe (VIADDMNMX, PRMT, LOP3), while the FMA pipe (IMAD)
+// idles.  Plain adds / subtracts / shift-and-ors are therefore written as mad.lo with a multiplier
+// taken from a kernel parameter (ptxas cannot fold it), which pins them to the FMA pipe.
+// Check inputs are staged per warp in shared memory by TMA bulk copies (see the check pass).
 #include <cstdlib>
 #include <string>
 
@@ -58,13 +61,8 @@ struct FloodI8Params {
     int jones, deg1clip;
     // opaque multipliers for FMA-pipe integer arithmetic (see header): -1, 1, -2, 255, 2^8, 2^16, 2^24
     int c_m1, c_one, c_m2, c_ff, c_sh8, c_sh16, c_sh24;
-    long long dephase_ns;   // experiment: > 0 delays the second CTA of every SM by this long, -1: until the first CTA's first check pass is done
 };
 
-#ifdef LDPC_I8_DEPHASE
-__device__ unsigned g_sm_arrivals[512];
-__device__ unsigned g_sm_flag[512];
-#endif
 
 struct Consts { int m1, one, m2, ff, sh[4]; };
 
@@ -110,13 +108,6 @@ __device__ __forceinline__ void st_lane(uint32_t* base, size_t node, int lane, c
     if (NW == 4) __stcg(reinterpret_cast<uint4*>(p), make_uint4(v.w[0], v.w[1 % NW], v.w[2 % NW], v.w[3 % NW]));
     else __stcg(p, v.w[0]);
 }
-
-// 16-byte asynchronous global -> shared copy (LDGSTS), L2 only
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- TMA bulk copy global -> shared, completion on an mbarrier (one elected lane issues it) ------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -226,21 +217,6 @@ __device__ __forceinline__ void check_word(uint32_t (&x)[D], uint32_t skip, cons
             r[0] = a[1];
             r[1] = a[0];
         } else {
-#ifdef LDPC_I8_OLD_FOLD
-            int acc = a[1];
-#pragma unroll
-            for (int i = 2; i < D; ++i) acc = gop(a[i], acc, tb, k);
-            r[0] = acc;
-            int P = a[0];                            // fold(x_0 .. x_{j-1})
-#pragma unroll
-            for (int j = 1; j < D; ++j) {
-                acc = P;
-#pragma unroll
-                for (int i = j + 1; i < D; ++i) acc = gop(a[i], acc, tb, k);
-                r[j] = acc;
-                if (j < D - 1) P = gop(a[j], P, tb, k);
-            }
-#else
             // Difference form of the same folds: a chain is carried as idx = (next input) - acc, the
             // table returns V[idx] = idx - U[idx], and the index of the following step is
             //   a' - max(acc + U[idx], 0) = min(V[idx] + (a' - a), a')
@@ -274,7 +250,6 @@ __device__ __forceinline__ void check_word(uint32_t (&x)[D], uint32_t skip, cons
                     r[j] = run(imad(dP, k.one, d1[j]), j + 1);      // a_{j+1} - P_j, then a_{j+2} ..
                 }
             }
-#endif
         }
 #pragma unroll
         for (int j = 0; j < D; ++j) {
@@ -442,10 +417,6 @@ __device__ __forceinline__ void var_class(uint32_t* __restrict__ msg, typename H
         for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int j = 0; j < D; ++j) w[u][j] = ld_lane<NW>(msg, (size_t)e[u][j], lane);
-#ifdef LDPC_I8_VPREF
-        int en[U][D], vn[U];
-        if (i + kWarps * U < count) load_idx(i + kWarps * U, en, vn);
-#endif
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (!ok[u]) continue;
@@ -475,16 +446,7 @@ __device__ __forceinline__ void var_class(uint32_t* __restrict__ msg, typename H
                 hbit[(size_t)e[u][j] * kLanes + lane] = (typename HBitsT<NW>::type)hb;
             }
         }
-#ifdef LDPC_I8_VPREF
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            v[u] = vn[u];
-#pragma unroll
-            for (int j = 0; j < D; ++j) e[u][j] = en[u][j];
-        }
-#else
         if (i + kWarps * U < count) load_idx(i + kWarps * U, e, v);
-#endif
     }
 }
 
@@ -531,12 +493,10 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
     __shared__ uint32_t s_unsat[kLanes];
     __shared__ uint32_t s_done[kLanes];
     __shared__ uint32_t s_skip;
-#ifndef LDPC_I8_NO_TMA
     __shared__ __align__(8) uint64_t s_bar[kWarps][2];     // one mbarrier per warp and stage
     if (lane_of_thread() == 0) { mbar_init(&s_bar[threadIdx.x >> 5][0], 1); mbar_init(&s_bar[threadIdx.x >> 5][1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     uint32_t bar_phase = 0;                                 // bit s = parity the next wait on stage s uses
-#endif
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t tile = blockIdx.x;
@@ -558,34 +518,6 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
     if (threadIdx.x < kLanes) { s_unsat[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
     if (threadIdx.x == 0) s_skip = 0;
     PROF_T(pt_init0);
-#ifdef LDPC_I8_DEPHASE
-    __shared__ int s_slot, s_smid;
-    if (threadIdx.x == 0) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        s_smid = (int)smid;
-        s_slot = (int)(atomicAdd(&g_sm_arrivals[smid], 1u) & 1u);
-    }
-    __syncthreads();
-    if (p.dephase_ns != 0 && s_slot == 1) {
-        if (threadIdx.x == 0) {
-            if (p.dephase_ns > 0) {
-                unsigned long long t0, t1;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                do { __nanosleep(2000); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while ((long long)(t1 - t0) < p.dephase_ns);
-            } else {
-                unsigned long long t0, t1;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                do {                                  // bounded: never wait more than 40 ms for a partner
-                    __nanosleep(2000);
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                } while (atomicAdd(&g_sm_flag[s_smid], 0u) == 0u && (long long)(t1 - t0) < 40000000ll);
-                atomicExch(&g_sm_flag[s_smid], 0u);
-            }
-        }
-        __syncthreads();
-    }
-#endif
 
     // flooding.rs:88-100: first variable messages are the quantised channel LLRs; the
     // "iteration 0" hard decisions are the raw LLR signs (flooding.rs:57).  Edge-parallel, four
@@ -615,8 +547,7 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
             // Per-warp double buffer in shared memory: the messages and hard bits of check c+kWarps stream
             // in while check c is being computed, at no register cost.  A check's D message lines (and its
             // D hard-bit lines) are contiguous in HBM, so one elected lane moves each with a single TMA bulk
-            // copy (cp.async.bulk) that completes on the stage's mbarrier; -DLDPC_I8_NO_TMA keeps the older
-            // per-lane 16-byte cp.async path for comparison.
+            // copy (cp.async.bulk) that completes on the stage's mbarrier.
             uint8_t* wbuf = dsm + (size_t)warp * 2 * kStageBytes;
             // row_ptr of the check after next is fetched one step early, so issuing a stage never waits on it
             auto row_of = [&](int c, int& e0o, int& dout) {
@@ -624,7 +555,6 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
                 e0o = __ldg(g.row_ptr + cc);
                 dout = __ldg(g.row_ptr + cc + 1) - e0o;
             };
-#ifndef LDPC_I8_NO_TMA
             auto issue = [&](int stage, int e0, int d) {
                 if (d <= MAXD && d > 0 && lane == 0) {
                     uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
@@ -634,21 +564,6 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
                     bulk_g2s(sb + kMsgBytes, hbit + (size_t)e0 * kLanes, hbytes, &s_bar[warp][stage]);
                 }
             };
-#else
-            auto issue = [&](int stage, int e0, int d) {
-                if (d <= MAXD) {
-                    uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
-                    if (!last) {
-                        const uint8_t* gm = reinterpret_cast<const uint8_t*>(msg + (size_t)e0 * kLanes * NW);
-                        for (int i = lane; i < d * 8 * NW; i += 32) cp_async16(sb + i * 16, gm + (size_t)i * 16);
-                    }
-                    const uint8_t* gh = reinterpret_cast<const uint8_t*>(hbit + (size_t)e0 * kLanes);
-                    const int hchunks = d * (int)sizeof(HB) * 2;                     // 32 lanes * sizeof(HB) / 16
-                    if (lane < hchunks) cp_async16(sb + kMsgBytes + lane * 16, gh + (size_t)lane * 16);
-                }
-                cp_async_commit();
-            };
-#endif
             int c = warp, stage = 0, e0c = 0, dc = 0, e0n = 0, dn = 0;
             if (c < g.m) {
                 row_of(c, e0c, dc);
@@ -658,7 +573,6 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
             for (; c < g.m; c += kWarps, stage ^= 1) {
                 const int e0 = e0c, d = dc;
                 e0c = e0n; dc = dn;
-#ifndef LDPC_I8_NO_TMA
                 if (c + kWarps < g.m) {
                     issue(stage ^ 1, e0c, dc);
                     row_of(c + 2 * kWarps, e0n, dn);
@@ -667,14 +581,6 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
                     mbar_wait(&s_bar[warp][stage], (bar_phase >> stage) & 1u);
                     bar_phase ^= 1u << stage;
                 }
-#else
-                if (c + kWarps < g.m) {
-                    issue(stage ^ 1, e0c, dc);
-                    row_of(c + 2 * kWarps, e0n, dn);
-                    cp_async_wait<1>();
-                } else cp_async_wait<0>();
-                __syncwarp();
-#endif
                 const uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
                 uint32_t hb = 0;
                 if (d > MAXD) {
@@ -713,9 +619,6 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
         __syncthreads();
         PROF_T(pt_c1);
         PROF_ADD(1, pt_c0, pt_c1);
-#ifdef LDPC_I8_DEPHASE
-        if (p.dephase_ns < 0 && it == 1 && s_slot == 0 && threadIdx.x == 0) atomicExch(&g_sm_flag[s_smid], 1u);
-#endif
         const uint32_t unsat = s_unsat[lane], done = s_done[lane];
         // frames whose hard decisions of iteration it-1 satisfy every check stop now
         // (flooding.rs:57-64 for it-1 == 0, :69-79 otherwise)
@@ -817,8 +720,6 @@ bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream) {
     p.g = L.graph; p.vc = L.classes;
     p.msg = L.msg; p.hbit = L.hbit; p.inq = L.inq; p.raw0 = L.raw0; p.final_hard = L.final_hard; p.iters = L.iters;
     p.max_iter = L.max_iter; p.jones = L.jones; p.deg1clip = L.deg1clip;
-    p.dephase_ns = 0;
-    if (const char* e = getenv("LDPC_I8_DEPHASE_US")) p.dephase_ns = atoll(e) < 0 ? -1 : atoll(e) * 1000;
     p.c_m1 = -1; p.c_one = 1; p.c_m2 = -2; p.c_ff = 0xff; p.c_sh8 = 1 << 8; p.c_sh16 = 1 << 16; p.c_sh24 = 1 << 24;
     if (L.words_per_lane == 4) launch_nw<4>(L, p, stream);
     else launch_nw<1>(L, p, stream);
