@@ -58,6 +58,7 @@ struct FloodI8Params {
     void* final_hard;       // [tiles][n][32]     snapshot taken when a frame stops
     int32_t* iters;         // [tiles*128*NW]     iterations, or -1 on failure
     int max_iter;
+    int num_tiles;
     int jones, deg1clip;
     // opaque multipliers for FMA-pipe integer arithmetic (see header): -1, 1, -2, 255, 2^8, 2^16, 2^24
     int c_m1, c_one, c_m2, c_ff, c_sh8, c_sh16, c_sh24;
@@ -72,7 +73,15 @@ struct Consts { int m1, one, m2, ff, sh[4]; };
 #ifndef LDPC_I8_MINBLOCKS
 #define LDPC_I8_MINBLOCKS 2
 #endif
-constexpr int kWarps = LDPC_I8_WARPS;            // warps per CTA
+#ifndef LDPC_I8_GROUPS
+#define LDPC_I8_GROUPS 1
+#endif
+constexpr int kWarps = LDPC_I8_WARPS;            // warps per tile (one warp group)
+// Warp groups per CTA.  2: a CTA owns two tiles and runs them half an iteration apart, in lockstep —
+// while group 0 is in its check pass (table reads, integer pipe) group 1 is in its variable pass
+// (HBM gathers) and vice versa, so the two passes overlap instead of competing with themselves.
+constexpr int kGroups = LDPC_I8_GROUPS;
+constexpr int kCtaThreads = kWarps * 32 * kGroups;
 
 #ifdef LDPC_I8_PROFILE
 // experiment-only: SM-clock cycles thread 0 of every CTA spent in {init, check pass, stop logic, variable pass}, [4] = CTA-iterations
@@ -86,6 +95,27 @@ __device__ unsigned long long g_i8_prof[8];
 constexpr int kMaxGenericD = 64;     // larger rows are rejected when the decoder is built
 
 __device__ __forceinline__ int lane_of_thread() { return threadIdx.x & 31; }
+// barriers of one warp group (named barrier 1 + group, kWarps * 32 threads); with one group per CTA they
+// are the plain CTA barriers
+__device__ __forceinline__ void group_sync(int grp) {
+    if (kGroups == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kWarps * 32) : "memory");
+}
+__device__ __forceinline__ int group_or(int grp, int pred) {
+    if (kGroups == 1) return __syncthreads_or(pred);
+    int r;
+    asm volatile("{\n.reg .pred p, q;\nsetp.ne.s32 q, %1, 0;\nbar.red.or.pred p, %2, %3, q;\nselp.s32 %0, 1, 0, p;\n}"
+                 : "=r"(r) : "r"(pred), "r"(grp + 1), "r"(kWarps * 32) : "memory");
+    return r;
+}
+__device__ __forceinline__ int group_and(int grp, int pred) {
+    if (kGroups == 1) return __syncthreads_and(pred);
+    int r;
+    asm volatile("{\n.reg .pred p, q;\nsetp.ne.s32 q, %1, 0;\nbar.red.and.pred p, %2, %3, q;\nselp.s32 %0, 1, 0, p;\n}"
+                 : "=r"(r) : "r"(pred), "r"(grp + 1), "r"(kWarps * 32) : "memory");
+    return r;
+}
+
 template <int NW> struct Lane { uint32_t w[NW]; };
 template <int NW> struct HBitsT { using type = uint8_t; };
 template <> struct HBitsT<4> { using type = uint16_t; };
@@ -481,25 +511,31 @@ __device__ __noinline__ void var_generic_class(uint32_t* __restrict__ msg, typen
 }
 
 template <int NW, bool AMIN, bool HLIM>
-__global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kernel(FloodI8Params p) {
+__global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS : 1) flood_i8_kernel(FloodI8Params p) {
     using HB = typename HBitsT<NW>::type;
     constexpr int MAXD = NW == 1 ? 10 : 8;          // check degrees with an unrolled register path
     constexpr uint32_t kAll = NW == 1 ? 0xfu : 0xffffu;
     constexpr int kFrames = kTileFrames * NW;
     constexpr int kMsgBytes = MAXD * kLanes * NW * 4;                 // one check's message lines
     constexpr int kStageBytes = kMsgBytes + MAXD * kLanes * (int)sizeof(HB);
-    extern __shared__ __align__(16) uint8_t dsm[];                    // [kWarps][2][kStageBytes]
+    extern __shared__ __align__(16) uint8_t dsm[];                    // [kGroups * kWarps][2][kStageBytes]
     __shared__ __align__(128) Tables tb;
-    __shared__ uint32_t s_unsat[kLanes];
-    __shared__ uint32_t s_done[kLanes];
-    __shared__ uint32_t s_skip;
-    __shared__ __align__(8) uint64_t s_bar[kWarps][2];     // one mbarrier per warp and stage
+    __shared__ uint32_t s_unsat_g[kGroups][kLanes];
+    __shared__ uint32_t s_done_g[kGroups][kLanes];
+    __shared__ uint32_t s_skip_g[kGroups];
+    __shared__ int s_fin[2][kGroups];                      // [step parity][group]: the group has finished its tile
+    __shared__ __align__(8) uint64_t s_bar[kGroups * kWarps][2];      // one mbarrier per warp and stage
     if (lane_of_thread() == 0) { mbar_init(&s_bar[threadIdx.x >> 5][0], 1); mbar_init(&s_bar[threadIdx.x >> 5][1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     uint32_t bar_phase = 0;                                 // bit s = parity the next wait on stage s uses
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, cta_warp = threadIdx.x >> 5;
+    const int grp = cta_warp / kWarps, warp = cta_warp % kWarps;      // warp group (tile) and warp within it
+    const size_t tile = (size_t)blockIdx.x * kGroups + grp;
+    const bool active = tile < (size_t)p.num_tiles;
+    uint32_t* const s_unsat = s_unsat_g[grp];
+    uint32_t* const s_done = s_done_g[grp];
+    uint32_t& s_skip = s_skip_g[grp];
     const DeviceGraph& g = p.g;
     const Consts kc = {p.c_m1, p.c_one, p.c_m2, p.c_ff, {1, p.c_sh8, p.c_sh16, p.c_sh24}};
     uint32_t* msg = p.msg + tile * (size_t)g.E * kLanes * NW;
@@ -515,14 +551,15 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
         tb.V[i] = (uint8_t)(max(d, 0) + table_T(abs(d)));
     }
     if (threadIdx.x < 128) tb.Tp[threadIdx.x] = (int8_t)table_T(threadIdx.x);
-    if (threadIdx.x < kLanes) { s_unsat[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
-    if (threadIdx.x == 0) s_skip = 0;
+    if (warp == 0) { s_unsat[lane] = 0; s_done[lane] = 0; }
+    if (warp == 0 && lane == 0) s_skip = 0;
+    __syncthreads();
     PROF_T(pt_init0);
 
     // flooding.rs:88-100: first variable messages are the quantised channel LLRs; the
     // "iteration 0" hard decisions are the raw LLR signs (flooding.rs:57).  Edge-parallel, four
     // independent edges in flight per warp.
-    for (int e0 = warp * 4; e0 < g.E; e0 += kWarps * 4) {
+    for (int e0 = warp * 4; active && e0 < g.E; e0 += kWarps * 4) {
         int v[4];
         Lane<NW> w[4];
         HB hb[4];
@@ -538,7 +575,14 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
     PROF_T(pt_init1);
     PROF_ADD(0, pt_init0, pt_init1);
 
-    for (int it = 1;; ++it) {
+    // A group alternates check pass (+ stop logic) and variable pass.  With two groups the CTA advances
+    // in steps: group g starts at step g, and a CTA-wide barrier ends every step, so the groups stay
+    // half an iteration apart for the whole decode.
+    int it = 1;
+    bool finished = !active, in_var = false;
+    for (int step = 0;; ++step) {
+      if (!finished && step >= grp) {
+        if (!in_var) {
         PROF_T(pt_c0);
         const bool last = it > p.max_iter;           // only the syndrome of iteration max_iter is left
         const uint32_t skip = s_skip;                // frame slots in which every lane has stopped
@@ -548,7 +592,7 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
             // in while check c is being computed, at no register cost.  A check's D message lines (and its
             // D hard-bit lines) are contiguous in HBM, so one elected lane moves each with a single TMA bulk
             // copy (cp.async.bulk) that completes on the stage's mbarrier.
-            uint8_t* wbuf = dsm + (size_t)warp * 2 * kStageBytes;
+            uint8_t* wbuf = dsm + (size_t)cta_warp * 2 * kStageBytes;
             // row_ptr of the check after next is fetched one step early, so issuing a stage never waits on it
             auto row_of = [&](int c, int& e0o, int& dout) {
                 const int cc = min(c, g.m - 1);
@@ -559,9 +603,9 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
                 if (d <= MAXD && d > 0 && lane == 0) {
                     uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
                     const uint32_t mb = last ? 0u : (uint32_t)d * kLanes * NW * 4, hbytes = (uint32_t)d * kLanes * (uint32_t)sizeof(HB);
-                    mbar_expect_tx(&s_bar[warp][stage], mb + hbytes);
-                    if (!last) bulk_g2s(sb, msg + (size_t)e0 * kLanes * NW, mb, &s_bar[warp][stage]);
-                    bulk_g2s(sb + kMsgBytes, hbit + (size_t)e0 * kLanes, hbytes, &s_bar[warp][stage]);
+                    mbar_expect_tx(&s_bar[cta_warp][stage], mb + hbytes);
+                    if (!last) bulk_g2s(sb, msg + (size_t)e0 * kLanes * NW, mb, &s_bar[cta_warp][stage]);
+                    bulk_g2s(sb + kMsgBytes, hbit + (size_t)e0 * kLanes, hbytes, &s_bar[cta_warp][stage]);
                 }
             };
             int c = warp, stage = 0, e0c = 0, dc = 0, e0n = 0, dn = 0;
@@ -578,7 +622,7 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
                     row_of(c + 2 * kWarps, e0n, dn);
                 }
                 if (d <= MAXD && d > 0) {
-                    mbar_wait(&s_bar[warp][stage], (bar_phase >> stage) & 1u);
+                    mbar_wait(&s_bar[cta_warp][stage], (bar_phase >> stage) & 1u);
                     bar_phase ^= 1u << stage;
                 }
                 const uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
@@ -616,7 +660,7 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
             }
         }
         if (synd) atomicOr(&s_unsat[lane], synd);
-        __syncthreads();
+        group_sync(grp);
         PROF_T(pt_c1);
         PROF_ADD(1, pt_c0, pt_c1);
         const uint32_t unsat = s_unsat[lane], done = s_done[lane];
@@ -625,7 +669,7 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
         uint32_t stop = ~unsat & ~done & kAll;
         uint32_t fail = 0;
         if (last) { fail = unsat & ~done & kAll; stop |= fail; }      // flooding.rs:81-85
-        const int any = __syncthreads_or(stop != 0);
+        const int any = group_or(grp, stop != 0);
         if (warp == 0) s_unsat[lane] = 0;
         if (any) {
             if (stop) {
@@ -654,11 +698,13 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
                 if (lane == 0) s_skip = all_done & kAll;
             }
         }
-        const int all = __syncthreads_and(((done | stop) & kAll) == kAll);
-        if (all || last) break;
+        const int all = group_and(grp, ((done | stop) & kAll) == kAll);
+        if (all || last) finished = true;
+        else in_var = true;
         PROF_T(pt_v0);
         PROF_ADD(2, pt_c1, pt_v0);
-
+        } else {
+        PROF_T(pt_v0);
         const bool jones = p.jones != 0, d1c = p.deg1clip != 0;
         const uint32_t vskip = s_skip;
         for (int k = 0; k < p.vc.num_classes; ++k) {
@@ -681,10 +727,24 @@ __global__ void __launch_bounds__(kWarps * 32, LDPC_I8_MINBLOCKS) flood_i8_kerne
             }
 #undef LDPC_VAR_CASE
         }
-        __syncthreads();
+        group_sync(grp);
         PROF_T(pt_v1);
         PROF_ADD(3, pt_v0, pt_v1);
         PROF_ADD(4, 0, 1);
+        in_var = false;
+        ++it;
+        }
+      }
+      if (kGroups == 1) {
+          if (finished) break;
+      } else {
+          if (warp == 0 && lane == 0) s_fin[step & 1][grp] = finished ? 1 : 0;
+          __syncthreads();                          // lockstep: both groups end the step together
+          bool all_fin = true;
+#pragma unroll
+          for (int gg = 0; gg < kGroups; ++gg) all_fin = all_fin && s_fin[step & 1][gg] != 0;
+          if (all_fin) break;
+      }
     }
 }
 
@@ -692,10 +752,10 @@ template <int NW, bool AMIN, bool HLIM>
 void launch_one(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t stream) {
     constexpr int MAXD = NW == 1 ? 10 : 8;
     constexpr size_t stage = (size_t)MAXD * kLanes * NW * 4 + (size_t)MAXD * kLanes * sizeof(typename HBitsT<NW>::type);
-    constexpr size_t smem = (size_t)kWarps * 2 * stage;
+    constexpr size_t smem = (size_t)kGroups * kWarps * 2 * stage;
     // per device and cheap: set on every launch (one process may drive several GPUs)
     cudaFuncSetAttribute(flood_i8_kernel<NW, AMIN, HLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    flood_i8_kernel<NW, AMIN, HLIM><<<dim3((unsigned)L.num_tiles), dim3(kWarps * 32), smem, stream>>>(p);
+    flood_i8_kernel<NW, AMIN, HLIM><<<dim3((unsigned)((L.num_tiles + kGroups - 1) / kGroups)), dim3(kCtaThreads), smem, stream>>>(p);
 }
 
 template <int NW>
@@ -719,7 +779,7 @@ bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream) {
     FloodI8Params p;
     p.g = L.graph; p.vc = L.classes;
     p.msg = L.msg; p.hbit = L.hbit; p.inq = L.inq; p.raw0 = L.raw0; p.final_hard = L.final_hard; p.iters = L.iters;
-    p.max_iter = L.max_iter; p.jones = L.jones; p.deg1clip = L.deg1clip;
+    p.max_iter = L.max_iter; p.num_tiles = L.num_tiles; p.jones = L.jones; p.deg1clip = L.deg1clip;
     p.c_m1 = -1; p.c_one = 1; p.c_m2 = -2; p.c_ff = 0xff; p.c_sh8 = 1 << 8; p.c_sh16 = 1 << 16; p.c_sh24 = 1 << 24;
     if (L.words_per_lane == 4) launch_nw<4>(L, p, stream);
     else launch_nw<1>(L, p, stream);

@@ -43,3 +43,17 @@ def test_gpu_matches_golden(tag, impl, alist, llrs, bits, its):
     out, got = Decoder(alist, impl).decode_batch(llrs, MAX_ITER)
     bad = int(((got != its) | (out != bits).any(axis=1)).sum())
     assert bad <= (0 if "i8" in impl else 1), f"{impl}: {bad} of {len(its)} frames differ from the golden vectors"
+
+
+HL_CASES = [c for c in CASES if c[1].startswith("HL")]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,impl,alist,llrs,bits,its", HL_CASES, ids=[f"{c[0]}-{c[1]}" for c in HL_CASES])
+def test_gpu_frame_per_cta_layered_matches_golden(tag, impl, alist, llrs, bits, its, monkeypatch):
+    """The same fixtures through K3q (frame per CTA, posteriors in shared memory), forced on these small codes."""
+    from ldpc_toolbox_b200 import Decoder
+    monkeypatch.setenv("LDPC_B200_LAYERED", "smem")
+    out, got = Decoder(alist, impl).decode_batch(llrs, MAX_ITER)
+    bad = int(((got != its) | (out != bits).any(axis=1)).sum())
+    assert bad <= (0 if "i8" in impl else 1), f"{impl}: {bad} of {len(its)} frames differ from the golden vectors"
