@@ -38,6 +38,8 @@
 // idles.  Plain adds / subtracts / shift-and-ors are therefore written as mad.lo with a multiplier
 // taken from a kernel parameter (ptxas cannot fold it), which pins them to the FMA pipe.
 // Check inputs are staged per warp in shared memory by TMA bulk copies (see the check pass).
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 #include <string>
 
@@ -419,7 +421,7 @@ template <int NW, int D, int U>
 __device__ __forceinline__ void var_class(uint32_t* __restrict__ msg, typename HBitsT<NW>::type* __restrict__ hbit,
                                           const uint32_t* __restrict__ inq, const int* __restrict__ vlist,
                                           const int* __restrict__ vedges, int count, bool jones, bool deg1clip,
-                                          uint32_t skip, int warp, int lane, const Consts& kc) {
+                                          uint32_t skip, int warp, int nwarps, int lane, const Consts& kc) {
     const VarConsts k = var_consts(D, jones);
     // indices of this warp's next group are fetched while the current group's lines are in flight
     auto load_idx = [&](int i, int (&e)[U][D], int (&v)[U]) {
@@ -435,7 +437,7 @@ __device__ __forceinline__ void var_class(uint32_t* __restrict__ msg, typename H
     if (i >= count) return;
     int e[U][D], v[U];
     load_idx(i, e, v);
-    for (; i < count; i += kWarps * U) {
+    for (; i < count; i += nwarps * U) {
         Lane<NW> w[U][D], inw[U];
         bool ok[U];
 #pragma unroll
@@ -476,7 +478,7 @@ __device__ __forceinline__ void var_class(uint32_t* __restrict__ msg, typename H
                 hbit[(size_t)e[u][j] * kLanes + lane] = (typename HBitsT<NW>::type)hb;
             }
         }
-        if (i + kWarps * U < count) load_idx(i + kWarps * U, e, v);
+        if (i + nwarps * U < count) load_idx(i + nwarps * U, e, v);
     }
 }
 
@@ -484,9 +486,9 @@ __device__ __forceinline__ void var_class(uint32_t* __restrict__ msg, typename H
 template <int NW>
 __device__ __noinline__ void var_generic_class(uint32_t* __restrict__ msg, typename HBitsT<NW>::type* __restrict__ hbit,
                                                const uint32_t* __restrict__ inq, const DeviceGraph& g,
-                                               const int* __restrict__ vlist, int count, bool jones, int warp, int lane,
-                                               const Consts& kc) {
-    for (int i = warp; i < count; i += kWarps) {
+                                               const int* __restrict__ vlist, int count, bool jones, int warp, int nwarps,
+                                               int lane, const Consts& kc) {
+    for (int i = warp; i < count; i += nwarps) {
         int v = __ldg(vlist + i);
         int p0 = __ldg(g.col_ptr + v), d = __ldg(g.col_ptr + v + 1) - p0;
         const int* ce = g.col_edge + p0;
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
     constexpr int kStageBytes = kMsgBytes + MAXD * kLanes * (int)sizeof(HB);
     extern __shared__ __align__(16) uint8_t dsm[];                    // [kGroups * kWarps][2][kStageBytes]
     __shared__ __align__(128) Tables tb;
-    __shared__ uint32_t s_unsat_g[kGroups][kLanes];
+    __shared__ uint32_t s_unsat_g[kGroups][2][kLanes];      // [iteration parity]: no reset race between the CTAs of a cluster
     __shared__ uint32_t s_done_g[kGroups][kLanes];
     __shared__ uint32_t s_skip_g[kGroups];
     __shared__ int s_fin[2][kGroups];                      // [step parity][group]: the group has finished its tile
@@ -529,11 +531,21 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     uint32_t bar_phase = 0;                                 // bit s = parity the next wait on stage s uses
 
+    // A thread-block cluster of C CTAs may own the tile (small batches: C x kWarps warps split every pass, a
+    // cluster barrier separates the passes, the syndrome words are OR-ed through distributed shared memory);
+    // C = 1 is the plain one-CTA-per-tile case of large batches.
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     const int lane = threadIdx.x & 31, cta_warp = threadIdx.x >> 5;
     const int grp = cta_warp / kWarps, warp = cta_warp % kWarps;      // warp group (tile) and warp within it
-    const size_t tile = (size_t)blockIdx.x * kGroups + grp;
+    const int gw = rank * kWarps + warp, nw = C * kWarps;             // this warp among the warps working on the tile
+    const size_t tile = (size_t)(blockIdx.x / (unsigned)C) * kGroups + grp;
     const bool active = tile < (size_t)p.num_tiles;
-    uint32_t* const s_unsat = s_unsat_g[grp];
+    auto pass_sync = [&]() {                                 // end of a pass of this tile
+        if (C > 1) cluster.sync();
+        else group_sync(grp);
+    };
     uint32_t* const s_done = s_done_g[grp];
     uint32_t& s_skip = s_skip_g[grp];
     const DeviceGraph& g = p.g;
@@ -551,7 +563,7 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
         tb.V[i] = (uint8_t)(max(d, 0) + table_T(abs(d)));
     }
     if (threadIdx.x < 128) tb.Tp[threadIdx.x] = (int8_t)table_T(threadIdx.x);
-    if (warp == 0) { s_unsat[lane] = 0; s_done[lane] = 0; }
+    if (warp == 0) { s_unsat_g[grp][0][lane] = 0; s_unsat_g[grp][1][lane] = 0; s_done[lane] = 0; }
     if (warp == 0 && lane == 0) s_skip = 0;
     __syncthreads();
     PROF_T(pt_init0);
@@ -559,7 +571,7 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
     // flooding.rs:88-100: first variable messages are the quantised channel LLRs; the
     // "iteration 0" hard decisions are the raw LLR signs (flooding.rs:57).  Edge-parallel, four
     // independent edges in flight per warp.
-    for (int e0 = warp * 4; active && e0 < g.E; e0 += kWarps * 4) {
+    for (int e0 = gw * 4; active && e0 < g.E; e0 += nw * 4) {
         int v[4];
         Lane<NW> w[4];
         HB hb[4];
@@ -571,7 +583,8 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
         for (int u = 0; u < 4; ++u)
             if (e0 + u < g.E) { st_lane<NW>(msg, (size_t)(e0 + u), lane, w[u]); hbit[(size_t)(e0 + u) * kLanes + lane] = hb[u]; }
     }
-    __syncthreads();
+    if (C > 1) cluster.sync();
+    else __syncthreads();
     PROF_T(pt_init1);
     PROF_ADD(0, pt_init0, pt_init1);
 
@@ -586,7 +599,10 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
         PROF_T(pt_c0);
         const bool last = it > p.max_iter;           // only the syndrome of iteration max_iter is left
         const uint32_t skip = s_skip;                // frame slots in which every lane has stopped
+        uint32_t* const s_unsat = s_unsat_g[grp][it & 1];
         uint32_t synd = 0;
+        // the lines about to be fetched through the async proxy (TMA) were written through the generic proxy
+        asm volatile("fence.proxy.async.global;" ::: "memory");
         {
             // Per-warp double buffer in shared memory: the messages and hard bits of check c+kWarps stream
             // in while check c is being computed, at no register cost.  A check's D message lines (and its
@@ -608,18 +624,18 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
                     bulk_g2s(sb + kMsgBytes, hbit + (size_t)e0 * kLanes, hbytes, &s_bar[cta_warp][stage]);
                 }
             };
-            int c = warp, stage = 0, e0c = 0, dc = 0, e0n = 0, dn = 0;
+            int c = gw, stage = 0, e0c = 0, dc = 0, e0n = 0, dn = 0;
             if (c < g.m) {
                 row_of(c, e0c, dc);
-                row_of(c + kWarps, e0n, dn);
+                row_of(c + nw, e0n, dn);
                 issue(0, e0c, dc);
             }
-            for (; c < g.m; c += kWarps, stage ^= 1) {
+            for (; c < g.m; c += nw, stage ^= 1) {
                 const int e0 = e0c, d = dc;
                 e0c = e0n; dc = dn;
-                if (c + kWarps < g.m) {
+                if (c + nw < g.m) {
                     issue(stage ^ 1, e0c, dc);
-                    row_of(c + 2 * kWarps, e0n, dn);
+                    row_of(c + 2 * nw, e0n, dn);
                 }
                 if (d <= MAXD && d > 0) {
                     mbar_wait(&s_bar[cta_warp][stage], (bar_phase >> stage) & 1u);
@@ -628,7 +644,7 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
                 const uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
                 uint32_t hb = 0;
                 if (d > MAXD) {
-                    for (int j = 0; j < d; ++j) hb ^= hbit[(size_t)(e0 + j) * kLanes + lane];
+                    for (int j = 0; j < d; ++j) hb ^= __ldcg(hbit + (size_t)(e0 + j) * kLanes + lane);
                     if (!last) check_generic<NW, AMIN, HLIM>(msg, (size_t)e0, d, lane, skip, tb, kc);
                 } else {
                     const HB* sh = reinterpret_cast<const HB*>(sb + kMsgBytes);
@@ -660,24 +676,26 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
             }
         }
         if (synd) atomicOr(&s_unsat[lane], synd);
-        group_sync(grp);
+        pass_sync();
         PROF_T(pt_c1);
         PROF_ADD(1, pt_c0, pt_c1);
-        const uint32_t unsat = s_unsat[lane], done = s_done[lane];
+        uint32_t unsat = s_unsat[lane];
+        for (int r = 1; r < C; ++r) unsat |= *cluster.map_shared_rank(&s_unsat[lane], (unsigned)((rank + r) % C));
+        const uint32_t done = s_done[lane];
         // frames whose hard decisions of iteration it-1 satisfy every check stop now
         // (flooding.rs:57-64 for it-1 == 0, :69-79 otherwise)
         uint32_t stop = ~unsat & ~done & kAll;
         uint32_t fail = 0;
         if (last) { fail = unsat & ~done & kAll; stop |= fail; }      // flooding.rs:81-85
         const int any = group_or(grp, stop != 0);
-        if (warp == 0) s_unsat[lane] = 0;
+        if (warp == 0) s_unsat_g[grp][(it & 1) ^ 1][lane] = 0;     // next iteration's words; their last readers are past the barrier above
         if (any) {
             if (stop) {
-                for (int v = warp; v < g.n; v += kWarps) {
+                for (int v = gw; v < g.n; v += nw) {
                     size_t o = (size_t)v * kLanes + lane;
                     int p0 = __ldg(g.col_ptr + v), p1 = __ldg(g.col_ptr + v + 1);
                     uint32_t hb;
-                    if (p1 > p0) hb = hbit[(size_t)__ldg(g.col_edge + p0) * kLanes + lane];
+                    if (p1 > p0) hb = __ldcg(hbit + (size_t)__ldg(g.col_edge + p0) * kLanes + lane);
                     else if (it == 1) hb = raw0[o];
                     else {                            // isolated variable: posterior = quantised input
                         hb = 0;
@@ -692,7 +710,7 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
             }
             if (warp == 0) {
                 for (int b = 0; b < 4 * NW; ++b)
-                    if (stop >> b & 1) iters[lane * 4 * NW + b] = (fail >> b & 1) ? -1 : it - 1;
+                    if (rank == 0 && (stop >> b & 1)) iters[lane * 4 * NW + b] = (fail >> b & 1) ? -1 : it - 1;
                 s_done[lane] = done | stop;
                 uint32_t all_done = __reduce_and_sync(0xffffffffu, done | stop);
                 if (lane == 0) s_skip = all_done & kAll;
@@ -712,7 +730,7 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
             const int* vl = p.vc.var_list + off;
             const int* ve = p.vc.var_edges + p.vc.edge_off[k];
 #define LDPC_VAR_CASE(D_, U_)                                                                                          \
-    case D_: var_class<NW, D_, U_>(msg, hbit, inq, vl, ve, cnt, jones, D_ == 1 && d1c, vskip, warp, lane, kc); break;
+    case D_: var_class<NW, D_, U_>(msg, hbit, inq, vl, ve, cnt, jones, D_ == 1 && d1c, vskip, gw, nw, lane, kc); break;
             #ifndef LDPC_I8_U3
 #define LDPC_I8_U3 2
 #endif
@@ -723,11 +741,11 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
             switch (deg) {
                 LDPC_VAR_CASE(1, U3) LDPC_VAR_CASE(2, U3) LDPC_VAR_CASE(3, U3) LDPC_VAR_CASE(4, U8)
                 LDPC_VAR_CASE(5, U8) LDPC_VAR_CASE(6, U8) LDPC_VAR_CASE(7, U8) LDPC_VAR_CASE(8, U8)
-                default: var_generic_class<NW>(msg, hbit, inq, g, vl, cnt, jones, warp, lane, kc); break;
+                default: var_generic_class<NW>(msg, hbit, inq, g, vl, cnt, jones, gw, nw, lane, kc); break;
             }
 #undef LDPC_VAR_CASE
         }
-        group_sync(grp);
+        pass_sync();
         PROF_T(pt_v1);
         PROF_ADD(3, pt_v0, pt_v1);
         PROF_ADD(4, 0, 1);
@@ -746,6 +764,7 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
           if (all_fin) break;
       }
     }
+    if (C > 1) cluster.sync();          // no CTA may leave while a peer can still read its shared memory
 }
 
 template <int NW, bool AMIN, bool HLIM>
@@ -755,7 +774,18 @@ void launch_one(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t str
     constexpr size_t smem = (size_t)kGroups * kWarps * 2 * stage;
     // per device and cheap: set on every launch (one process may drive several GPUs)
     cudaFuncSetAttribute(flood_i8_kernel<NW, AMIN, HLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    flood_i8_kernel<NW, AMIN, HLIM><<<dim3((unsigned)((L.num_tiles + kGroups - 1) / kGroups)), dim3(kCtaThreads), smem, stream>>>(p);
+    const int C = (kGroups == 1 && L.cluster >= 1 && L.cluster <= 8) ? L.cluster : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((L.num_tiles + kGroups - 1) / kGroups) * (unsigned)C);
+    cfg.blockDim = dim3(kCtaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, flood_i8_kernel<NW, AMIN, HLIM>, p);
 }
 
 template <int NW>

@@ -160,3 +160,23 @@ def test_dvbs2_normal_r12_north_star(oracle):
                            for i, e in enumerate((0.5, 1.1, 1.25, 2.5))])
     its = compare(oracle, alist, "Minstarapproxi8", llrs, 25, out_len=32400)
     assert (its == -1).any() and (its > 0).any()
+
+
+@pytest.mark.parametrize("cluster", ["1", "2", "8"])
+@pytest.mark.parametrize("impl", ["Minstarapproxi8", "Aminstari8JonesPartialHardLimitDeg1Clip"])
+def test_cluster_sizes(oracle, impl, cluster, monkeypatch):
+    """Small batches run one thread-block cluster per tile (checks / variables split over its CTAs, syndrome
+    words OR-ed through distributed shared memory); every cluster size must give the single-CTA answer."""
+    monkeypatch.setenv("LDPC_B200_CLUSTER", cluster)
+    rng = np.random.default_rng(77)
+    alist = helpers.random_code_alist(rng, 200, 80, col_w=[1, 2, 3, 4, 9], extra_heavy_rows=2)
+    cws = np.zeros((300, 200), dtype=np.uint8)
+    llrs = np.concatenate([helpers.awgn_llrs(rng, cws[:100], s) for s in (0.4, 0.8, 1.3)])
+    its = compare(oracle, alist, impl, llrs, 15, label=f"cluster {cluster} ")
+    assert (its > 0).any()
+    # and on a real code with early termination spread over many iterations
+    alist = codes.alist_for("dvbs2:R1_2short")
+    n, k = 16200, 7200
+    enc = oracle.encoder(alist)
+    msgs, cw = helpers.encoded_frames(enc, rng, k, n, 150)
+    compare(oracle, alist, impl, helpers.awgn_llrs(rng, cw, helpers.sigma_for(1.3, k / n)), 25, label=f"cluster {cluster} short ")
