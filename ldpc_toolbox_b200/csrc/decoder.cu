@@ -412,7 +412,7 @@ private:
             fl.raw0 = d_hard_.p; fl.final_hard = d_final_.p; fl.iters = d_iters_tile_.p; fl.max_iter = max_iter;
             fl.aminstar = impl_.rule == Rule::Aminstar; fl.jones = impl_.jones; fl.hardlimit = impl_.hardlimit; fl.deg1clip = impl_.deg1clip;
             fl.cluster = 1;
-            while (fl.cluster < 8 && tiles * fl.cluster * 2 <= 2 * sm_count_) fl.cluster *= 2;      // up to ~2 CTAs per SM
+            while (fl.cluster < 16 && tiles * fl.cluster * 2 <= 2 * sm_count_) fl.cluster *= 2;     // up to ~2 CTAs per SM
             if (const char* e = getenv("LDPC_B200_CLUSTER")) fl.cluster = atoi(e);
             if (!launch_flood_i8(fl, s)) return false;
         } else {

@@ -71,7 +71,7 @@ struct FloodI8Launch {
     int32_t* iters;
     int max_iter;
     bool aminstar, jones, hardlimit, deg1clip;
-    int cluster;             // CTAs per tile (thread-block cluster of 1, 2, 4 or 8): small batches fill the GPU this way
+    int cluster;             // CTAs per tile (thread-block cluster of 1 .. 16): small batches fill the GPU this way
 };
 bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream);
 int flood_i8_max_row_degree();

@@ -774,17 +774,24 @@ void launch_one(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t str
     constexpr size_t smem = (size_t)kGroups * kWarps * 2 * stage;
     // per device and cheap: set on every launch (one process may drive several GPUs)
     cudaFuncSetAttribute(flood_i8_kernel<NW, AMIN, HLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int C = (kGroups == 1 && L.cluster >= 1 && L.cluster <= 8) ? L.cluster : 1;
+    int C = (kGroups == 1 && L.cluster >= 1 && L.cluster <= 16) ? L.cluster : 1;
+    if (C > 8) cudaFuncSetAttribute(flood_i8_kernel<NW, AMIN, HLIM>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((L.num_tiles + kGroups - 1) / kGroups) * (unsigned)C);
     cfg.blockDim = dim3(kCtaThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    for (;; C /= 2) {                                   // a 16-CTA cluster needs a GPC with 16 free slots: fall back to 8, 4, ..
+        cfg.gridDim = dim3((unsigned)((L.num_tiles + kGroups - 1) / kGroups) * (unsigned)C);
+        attr[0].val.clusterDim.x = (unsigned)C;
+        int fit = 0;
+        if (C == 1 || (cudaOccupancyMaxActiveClusters(&fit, flood_i8_kernel<NW, AMIN, HLIM>, &cfg) == cudaSuccess && fit > 0)) break;
+        cudaGetLastError();
+    }
     cudaLaunchKernelEx(&cfg, flood_i8_kernel<NW, AMIN, HLIM>, p);
 }
 

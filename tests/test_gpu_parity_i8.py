@@ -162,7 +162,7 @@ def test_dvbs2_normal_r12_north_star(oracle):
     assert (its == -1).any() and (its > 0).any()
 
 
-@pytest.mark.parametrize("cluster", ["1", "2", "8"])
+@pytest.mark.parametrize("cluster", ["1", "2", "8", "16"])
 @pytest.mark.parametrize("impl", ["Minstarapproxi8", "Aminstari8JonesPartialHardLimitDeg1Clip"])
 def test_cluster_sizes(oracle, impl, cluster, monkeypatch):
     """Small batches run one thread-block cluster per tile (checks / variables split over its CTAs, syndrome
