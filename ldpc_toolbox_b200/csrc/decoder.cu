@@ -57,6 +57,8 @@ public:
         if (h2d_stream_) cudaStreamDestroy(h2d_stream_);
         if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
         for (auto& e : ev_) if (e) cudaEventDestroy(e);
+        if (ev_hist_) cudaEventDestroy(ev_hist_);
+        if (h_hist_) cudaFreeHost(h_hist_);
         for (int b = 0; b < 2; ++b)
             for (cudaEvent_t e : {ev_copied_[b], ev_ingested_[b], ev_emitted_[b], ev_drained_[b]}) if (e) cudaEventDestroy(e);
     }
@@ -115,6 +117,7 @@ public:
         max_tiles_opt_ = opt.max_tiles;
         nw_opt_ = opt.words_per_lane;
         if (const char* e = getenv("LDPC_B200_NW")) nw_opt_ = atoi(e);
+        if (const char* e = getenv("LDPC_B200_TWO_STAGE")) two_stage_ = atoi(e) != 0;
         return true;
     }
 
@@ -383,15 +386,18 @@ private:
         return true;
     }
 
-    bool run_chunk(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
-                   size_t out_len, size_t out_stride, int32_t* d_iters, cudaStream_t s, cudaEvent_t after_ingest = nullptr) {
+    // One ingest -> BP kernel -> emit pass over nf frames.  ev_begin / ev_end select which of the four timing
+    // events this pass records (a two-stage chunk spreads them over its passes).
+    bool run_pass(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
+                  size_t out_len, size_t out_stride, int32_t* d_iters, cudaStream_t s, cudaEvent_t after_ingest = nullptr,
+                  bool ev_begin = true, bool ev_end = true) {
         if (use_smem_layered_) return run_chunk_smem_layered(d_llrs, is_f64, llrs_len, nf, max_it, d_out, out_len, out_stride, d_iters, s, after_ingest);
         const int nw = pick_nw(nf);
         const size_t tf = (size_t)kTileFrames * nw;
         const int tiles = (int)((nf + tf - 1) / tf);
         if (!ensure_workspace((size_t)tiles, nw)) return false;
         if (!d_iters_tile_.ensure((size_t)tiles * tf)) return false;
-        cudaEventRecord(ev_[0], s);
+        if (ev_begin) cudaEventRecord(ev_[0], s);
         IngestLaunch in{};
         in.llrs = d_llrs; in.is_f64 = is_f64; in.llrs_len = llrs_len; in.nframes = nf; in.n = g_.n;
         in.src_map = punct_ ? d_src_map_.p : nullptr; in.num_tiles = tiles; in.words_per_lane = nw;
@@ -401,7 +407,7 @@ private:
         else if (impl_.dtype == Dtype::F64) in.in_f64 = reinterpret_cast<double*>(d_inq_.p);
         else in.in_i16 = reinterpret_cast<int16_t*>(d_inq_.p);
         if (!launch_ingest(in, s)) return false;
-        cudaEventRecord(ev_[1], s);
+        if (ev_begin) cudaEventRecord(ev_[1], s);
         if (after_ingest) cudaEventRecord(after_ingest, s);
         // a graph the min* rules panic on: run only the pre-check; everything else reports -2
         const int max_iter = panics_ ? 0 : (int)std::min<uint32_t>(max_it, 0x7ffffff0u);
@@ -428,7 +434,7 @@ private:
             if (const char* e = getenv("LDPC_B200_CLUSTER")) gl.cluster = atoi(e);
             if (!(kind_ == Kind::FloodFloat ? launch_flood_float(gl, s) : launch_layered(gl, s))) return false;
         }
-        cudaEventRecord(ev_[2], s);
+        if (ev_end) cudaEventRecord(ev_[2], s);
         EmitLaunch em{};
         em.final_hard = d_final_.p; em.n = g_.n; em.num_tiles = tiles; em.words_per_lane = nw; em.nframes = nf; em.out = d_out; em.out_len = out_len;
         em.out_stride = out_stride;
@@ -437,13 +443,97 @@ private:
         if (panics_ && max_it > 0) {
             if (!launch_mark_panics(d_iters, nf, s)) return false;
         }
-        cudaEventRecord(ev_[3], s);
+        if (ev_end) cudaEventRecord(ev_[3], s);
         stats_.kernel_launches += 3;
         timed_ = true;
         return true;
     }
 
+    // ---- straggler re-decode ----------------------------------------------------------------------
+    // A tile runs until its slowest frame stops, so at operating points where most frames converge
+    // early a few stragglers make every tile pay max_iterations.  When the iteration histogram of the
+    // previous chunk says it pays off, a chunk is decoded in two stages: every frame for at most m1
+    // iterations, then the frames still unconverged are gathered into a small dense batch and decoded
+    // again FROM THEIR LLRs with the full iteration budget.  Decoding is deterministic and frames are
+    // independent, so words and iteration counts are exactly those of a single pass.
+    uint32_t two_stage_m1(uint32_t max_it, size_t nf) {
+        if (!two_stage_ || panics_ || use_smem_layered_ || kind_ == Kind::Layered || max_it < 8 || max_it > 127) return 0;
+        const size_t tf = (size_t)kTileFrames * pick_nw(nf);
+        if (nf < 8 * tf || !hist_valid_ || hist_max_it_ != max_it) return 0;
+        cudaEventSynchronize(ev_hist_);
+        double total = 0;
+        for (uint32_t b = 0; b <= max_it; ++b) total += (double)h_hist_[b];
+        if (total < 1) return 0;
+        // gt[M] = fraction of frames that need more than M iterations (failures sit in bin max_it)
+        double best_cost = 1e300, tail = 0, single = (double)max_it;
+        uint32_t best_m = 0;
+        std::vector<double> gt((size_t)max_it + 1, 0.0);
+        for (uint32_t m = max_it; m-- > 0;) { tail += (double)h_hist_[m + 1]; gt[m] = tail / total; }
+        for (uint32_t m = 1; m < max_it; ++m) {
+            if (gt[m] < 0.5 / (double)tf && single == (double)max_it) single = (double)m;     // a tile's slowest frame, roughly
+            const double cost = (double)m + gt[m] * (double)max_it;
+            if (cost < best_cost) { best_cost = cost; best_m = m; }
+        }
+        return best_cost < 0.9 * single ? best_m : 0;
+    }
+
+    bool run_chunk(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
+                   size_t out_len, size_t out_stride, int32_t* d_iters, cudaStream_t s, cudaEvent_t after_ingest = nullptr) {
+        const uint32_t m1 = two_stage_m1(max_it, nf);
+        if (m1 == 0) {
+            if (!run_pass(d_llrs, is_f64, llrs_len, nf, max_it, d_out, out_len, out_stride, d_iters, s, after_ingest)) return false;
+            return record_histogram(d_iters, nf, max_it, s);
+        }
+        const size_t esz = is_f64 ? 8 : 4;
+        if (!run_pass(d_llrs, is_f64, llrs_len, nf, m1, d_out, out_len, out_stride, d_iters, s, nullptr, true, false)) return false;
+        if (!d_fail_idx_.ensure(nf + 1)) return false;
+        LDPC_CUDA_CHECK(cudaMemsetAsync(d_fail_idx_.p + nf, 0, sizeof(int32_t), s));
+        if (!launch_collect_failed(d_iters, nf, d_fail_idx_.p, d_fail_idx_.p + nf, s)) return false;
+        int32_t count = 0;
+        LDPC_CUDA_CHECK(cudaMemcpyAsync(&count, d_fail_idx_.p + nf, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        LDPC_CUDA_CHECK(cudaStreamSynchronize(s));
+        const size_t tf = (size_t)kTileFrames * pick_nw(nf);
+        const size_t cap = std::max(tf, (nf / 4 + tf - 1) / tf * tf);               // stage-2 sub-batch, whole tiles
+        if (count > 0) {
+            const size_t sub = std::min<size_t>(cap, (size_t)count);
+            if (!d_llrs2_.ensure(sub * llrs_len * esz) || !d_out2_.ensure(std::max<size_t>(sub * out_len, 1)) || !d_iters2_.ensure(sub)) return false;
+        }
+        for (size_t off = 0; off < (size_t)count; off += cap) {
+            const size_t c = std::min(cap, (size_t)count - off);
+            const bool last = off + c >= (size_t)count;
+            if (!launch_gather_rows(d_llrs, llrs_len * esz, d_fail_idx_.p + off, c, d_llrs2_.p, s)) return false;
+            if (!run_pass(d_llrs2_.p, is_f64, llrs_len, c, max_it, d_out2_.p, out_len, out_len, d_iters2_.p, s, nullptr, false, last)) return false;
+            if (!launch_scatter_results(d_out2_.p, out_len, d_iters2_.p, d_fail_idx_.p + off, c, d_out, out_stride, d_iters, s)) return false;
+        }
+        if (count == 0) { cudaEventRecord(ev_[2], s); cudaEventRecord(ev_[3], s); }
+        if (after_ingest) cudaEventRecord(after_ingest, s);        // the caller's LLRs were still needed by the gathers
+        stats_.kernel_launches += 1 + (count > 0 ? 2 : 0);
+        ++two_stage_chunks_;
+        return record_histogram(d_iters, nf, max_it, s);
+    }
+
+    bool record_histogram(const int32_t* d_iters, size_t nf, uint32_t max_it, cudaStream_t s) {
+        if (!two_stage_ || use_smem_layered_ || kind_ == Kind::Layered || max_it > 127) return true;
+        if (!d_hist_.ensure(128)) return false;
+        if (!h_hist_) {
+            LDPC_CUDA_CHECK(cudaMallocHost(&h_hist_, 128 * sizeof(unsigned int)));
+            LDPC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_hist_, cudaEventDisableTiming));
+        }
+        LDPC_CUDA_CHECK(cudaMemsetAsync(d_hist_.p, 0, 128 * sizeof(unsigned int), s));
+        if (!launch_iter_histogram(d_iters, nf, max_it, d_hist_.p, s)) return false;
+        LDPC_CUDA_CHECK(cudaMemcpyAsync(h_hist_, d_hist_.p, 128 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+        LDPC_CUDA_CHECK(cudaEventRecord(ev_hist_, s));
+        hist_valid_ = true;
+        hist_max_it_ = max_it;
+        return true;
+    }
+
     bool launch_mark_panics(int32_t* d_iters, size_t nf, cudaStream_t s);
+    bool launch_collect_failed(const int32_t* d_iters, size_t nf, int32_t* idx, int32_t* count, cudaStream_t s);
+    bool launch_gather_rows(const void* src, size_t row_bytes, const int32_t* idx, size_t count, void* dst, cudaStream_t s);
+    bool launch_scatter_results(const uint8_t* out2, size_t out_len, const int32_t* iters2, const int32_t* idx, size_t count,
+                                uint8_t* out, size_t out_stride, int32_t* iters, cudaStream_t s);
+    bool launch_iter_histogram(const int32_t* d_iters, size_t nf, uint32_t max_it, unsigned int* hist, cudaStream_t s);
 
 public:
     // resolves the event timings of the last chunk (synchronises the stream)
@@ -481,7 +571,14 @@ private:
     int smem_threads_ = 256;
     DevBuf<uint8_t> d_msg_, d_inq_;
     DevBuf<uint8_t> d_hbit_, d_hard_, d_final_, d_stage_in_[2], d_stage_out_[2];
-    DevBuf<int32_t> d_iters_tile_, d_stage_iters_[2];
+    DevBuf<int32_t> d_iters_tile_, d_stage_iters_[2], d_fail_idx_, d_iters2_;
+    DevBuf<uint8_t> d_llrs2_, d_out2_;
+    DevBuf<unsigned int> d_hist_;
+    unsigned int* h_hist_ = nullptr;
+    cudaEvent_t ev_hist_ = nullptr;
+    bool two_stage_ = true, hist_valid_ = false;
+    uint32_t hist_max_it_ = 0;
+    long long two_stage_chunks_ = 0;
     cudaStream_t h2d_stream_ = nullptr, d2h_stream_ = nullptr;
     cudaEvent_t ev_copied_[2] = {}, ev_ingested_[2] = {}, ev_emitted_[2] = {}, ev_drained_[2] = {};
 };
@@ -489,6 +586,65 @@ private:
 __global__ void mark_panics_kernel(int32_t* iters, size_t nf) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nf && iters[i] < 0) iters[i] = -2;
+}
+
+// frames that did not converge within the first stage, in arbitrary order
+__global__ void collect_failed_kernel(const int32_t* iters, size_t nf, int32_t* idx, int32_t* count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool f = i < nf && iters[i] < 0;
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    int base = 0;
+    const int lane = threadIdx.x & 31;
+    if (lane == 0 && m) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (f) idx[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+}
+
+__global__ void gather_rows_kernel(const uint32_t* src, size_t row_words, const int32_t* idx, uint32_t* dst) {
+    const uint32_t* s = src + (size_t)idx[blockIdx.x] * row_words;
+    uint32_t* d = dst + (size_t)blockIdx.x * row_words;
+    for (size_t w = threadIdx.x; w < row_words; w += blockDim.x) d[w] = s[w];
+}
+
+__global__ void scatter_results_kernel(const uint8_t* out2, size_t out_len, const int32_t* iters2, const int32_t* idx, uint8_t* out,
+                                       size_t out_stride, int32_t* iters) {
+    const size_t f = (size_t)idx[blockIdx.x];
+    const uint8_t* s = out2 + (size_t)blockIdx.x * out_len;
+    uint8_t* d = out + f * out_stride;
+    for (size_t b = threadIdx.x; b < out_len; b += blockDim.x) d[b] = s[b];
+    if (threadIdx.x == 0) iters[f] = iters2[blockIdx.x];
+}
+
+__global__ void iter_histogram_kernel(const int32_t* iters, size_t nf, uint32_t max_it, unsigned int* hist) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    const int32_t it = iters[i];
+    atomicAdd(&hist[it < 0 || (uint32_t)it > max_it ? max_it : (uint32_t)it], 1u);
+}
+
+bool GpuDecoder::launch_collect_failed(const int32_t* d_iters, size_t nf, int32_t* idx, int32_t* count, cudaStream_t s) {
+    collect_failed_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(d_iters, nf, idx, count);
+    LDPC_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+bool GpuDecoder::launch_gather_rows(const void* src, size_t row_bytes, const int32_t* idx, size_t count, void* dst, cudaStream_t s) {
+    gather_rows_kernel<<<(unsigned)count, 256, 0, s>>>(static_cast<const uint32_t*>(src), row_bytes / 4, idx, static_cast<uint32_t*>(dst));
+    LDPC_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+bool GpuDecoder::launch_scatter_results(const uint8_t* out2, size_t out_len, const int32_t* iters2, const int32_t* idx, size_t count,
+                                        uint8_t* out, size_t out_stride, int32_t* iters, cudaStream_t s) {
+    scatter_results_kernel<<<(unsigned)count, 256, 0, s>>>(out2, out_len, iters2, idx, out, out_stride, iters);
+    LDPC_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
+bool GpuDecoder::launch_iter_histogram(const int32_t* d_iters, size_t nf, uint32_t max_it, unsigned int* hist, cudaStream_t s) {
+    iter_histogram_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(d_iters, nf, max_it, hist);
+    LDPC_CUDA_CHECK(cudaGetLastError());
+    return true;
 }
 
 bool GpuDecoder::launch_mark_panics(int32_t* d_iters, size_t nf, cudaStream_t s) {

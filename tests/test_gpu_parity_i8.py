@@ -180,3 +180,30 @@ def test_cluster_sizes(oracle, impl, cluster, monkeypatch):
     enc = oracle.encoder(alist)
     msgs, cw = helpers.encoded_frames(enc, rng, k, n, 150)
     compare(oracle, alist, impl, helpers.awgn_llrs(rng, cw, helpers.sigma_for(1.3, k / n)), 25, label=f"cluster {cluster} short ")
+
+
+def test_straggler_redecode_is_exact(oracle, monkeypatch):
+    """Two-stage chunks (decoder.cu): after the first call has filled the iteration histogram, frames that
+    do not converge within m1 iterations are gathered and decoded again from their LLRs.  Words and iteration
+    counts must be those of a single pass (and of the CPU checker)."""
+    alist = codes.alist_for("dvbs2:R1_2short")
+    n, k = 16200, 7200
+    rng = np.random.default_rng(91)
+    enc = oracle.encoder(alist)
+    msgs, cw = helpers.encoded_frames(enc, rng, k, n, 64)
+    llrs = helpers.awgn_llrs(rng, cw[np.arange(2048) % 64], helpers.sigma_for(1.55, k / n))
+    dec = Decoder(alist, "Minstarapproxi8")
+    out1, it1 = dec.decode_batch(llrs, 30, output_len=k)            # no histogram yet: one pass
+    l1 = dec.last_timing()["kernel_launches"]
+    out2, it2 = dec.decode_batch(llrs, 30, output_len=k)            # two stages
+    l2 = dec.last_timing()["kernel_launches"] - l1
+    assert l2 > l1, "the second call was expected to run in two stages"
+    assert (it1 == it2).all() and (out1 == out2).all()
+    assert (it1 == -1).any() and (it1 > 0).any()
+    rout, rits = oracle.decoder(alist, "Minstarapproxi8").decode_batch(llrs[:512], 30, out_len=k)
+    assert (rits == it2[:512]).all() and (rout == out2[:512]).all()
+    monkeypatch.setenv("LDPC_B200_TWO_STAGE", "0")
+    ref = Decoder(alist, "Minstarapproxi8")
+    ref.decode_batch(llrs, 30, output_len=k)
+    out3, it3 = ref.decode_batch(llrs, 30, output_len=k)
+    assert (it3 == it2).all() and (out3 == out2).all()
