@@ -576,7 +576,7 @@ private:
     DevBuf<unsigned int> d_hist_;
     unsigned int* h_hist_ = nullptr;
     cudaEvent_t ev_hist_ = nullptr;
-    bool two_stage_ = true, hist_valid_ = false;
+    bool two_stage_ = false, hist_valid_ = false;      // opt-in (LDPC_B200_TWO_STAGE=1): exact, but measured no faster on DVB-S2
     uint32_t hist_max_it_ = 0;
     long long two_stage_chunks_ = 0;
     cudaStream_t h2d_stream_ = nullptr, d2h_stream_ = nullptr;

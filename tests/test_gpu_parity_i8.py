@@ -192,6 +192,7 @@ def test_straggler_redecode_is_exact(oracle, monkeypatch):
     enc = oracle.encoder(alist)
     msgs, cw = helpers.encoded_frames(enc, rng, k, n, 64)
     llrs = helpers.awgn_llrs(rng, cw[np.arange(2048) % 64], helpers.sigma_for(1.55, k / n))
+    monkeypatch.setenv("LDPC_B200_TWO_STAGE", "1")                  # opt-in
     dec = Decoder(alist, "Minstarapproxi8")
     out1, it1 = dec.decode_batch(llrs, 30, output_len=k)            # no histogram yet: one pass
     l1 = dec.last_timing()["kernel_launches"]
