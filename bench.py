@@ -190,7 +190,9 @@ def run_ours(args):
         avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
     except Exception:
         avail = 0
-    while e2e_frames > 128 and e2e_frames * (N * 4 + K_INFO) > 0.25 * avail:    # pinned buffers stay below a quarter of host RAM (an 88 GB pin got the process OOM-killed)
+    # one process pins at most a quarter of the available host RAM (an 88 GB pin once got the process
+    # OOM-killed), and all ranks of the node together at most 40 % (they pin at the same time)
+    while e2e_frames > 128 and e2e_frames * (N * 4 + K_INFO) > min(0.25 * avail, 0.4 * avail / world):
         e2e_frames //= 2
     h_llrs = torch.empty((e2e_frames, N), dtype=torch.float32, pin_memory=True)
     for f0 in range(0, e2e_frames, frames):
