@@ -14,9 +14,10 @@ tail -c 2500 gpurun_out/chk_bench.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_e_launches_raw.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/chk_bench_under_ncu.log 2>&1
 [ -n "$SKIP_FULL_NCU" ] && exit 0
-# full capture of the dominant kernel (one launch, 25 iterations, bench-sized batch)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:flood_i8 -s 1 -c 1 -f -o gpurun_out/r01_e_flood_i8 \
-    python tools/quick_bench.py --tiles 1184 --iters 25 --mean 2.24 --std 2.12 --signs 1 --reps 1 > gpurun_out/chk_ncu_k1.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:layered_smem -s 1 -c 1 -f -o gpurun_out/r01_e_layered_smem \
     python tools/bench_configs.py --configs c2 --points=-0.5 --reps 1 > gpurun_out/chk_ncu_k3q.log 2>&1
+[ -n "$SKIP_K1_FULL_NCU" ] && exit 0
+# full capture of the dominant kernel (one launch, 25 iterations, bench-sized batch; ~7 minutes of replays)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:flood_i8 -s 1 -c 1 -f -o gpurun_out/r01_e_flood_i8 \
+    python tools/quick_bench.py --tiles 1184 --iters 25 --mean 2.24 --std 2.12 --signs 1 --reps 1 > gpurun_out/chk_ncu_k1.log 2>&1
 ls -la gpurun_out/*.ncu-rep
