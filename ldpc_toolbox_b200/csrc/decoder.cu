@@ -309,7 +309,8 @@ private:
 
     // ELL layout of the level schedule for layered_smem.cu
     bool build_ell() {
-        std::vector<int> row_base((size_t)g_.m), row_stride((size_t)g_.m), row_deg((size_t)g_.m), ell_col;
+        std::vector<int> row_deg((size_t)g_.m), ell_col;
+        std::vector<int> level_ell((size_t)num_levels_), level_deg((size_t)num_levels_);
         size_t off = 0;
         int widest = 1;
         for (int l = 0; l < num_levels_; ++l) {
@@ -319,12 +320,13 @@ private:
                 const int c = h_level_rows_[(size_t)i];
                 maxd = std::max(maxd, g_.row_ptr[(size_t)c + 1] - g_.row_ptr[(size_t)c]);
             }
+            level_ell[(size_t)l] = (int)off;
+            level_deg[(size_t)l] = maxd;
             ell_col.resize(off + (size_t)maxd * nrows, 0);
             for (int i = r0; i < r1; ++i) {
                 const int c = h_level_rows_[(size_t)i], e0 = g_.row_ptr[(size_t)c], d = g_.row_ptr[(size_t)c + 1] - e0;
-                row_base[(size_t)i] = (int)(off + (size_t)(i - r0));
-                row_stride[(size_t)i] = nrows;
                 row_deg[(size_t)i] = d;
+                if (d != maxd) level_deg[(size_t)l] = -1;
                 for (int j = 0; j < d; ++j) ell_col[off + (size_t)j * nrows + (size_t)(i - r0)] = g_.col_idx[(size_t)e0 + j];
             }
             off += (size_t)maxd * nrows;
@@ -333,10 +335,12 @@ private:
         if (off > 0x7fffffffu) { set_last_error("level schedule too large"); return false; }
         ell_size_ = std::max<size_t>(off, 1);
         smem_threads_ = std::min(256, std::max(64, (widest + 31) / 32 * 32));      // layered_smem_impl.cuh: at most 256
-        if (!d_row_base_.upload(row_base) || !d_row_stride_.upload(row_stride) || !d_row_deg_.upload(row_deg) || !d_ell_col_.upload(ell_col))
+        if (const char* e = getenv("LDPC_B200_K3Q_THREADS")) smem_threads_ = std::min(256, std::max(32, atoi(e) / 32 * 32));
+        if (!d_row_deg_.upload(row_deg) || !d_ell_col_.upload(ell_col) || !d_level_ell_.upload(level_ell) || !d_level_deg_.upload(level_deg))
             return false;
-        sg_.n = g_.n; sg_.m = g_.m; sg_.num_levels = num_levels_; sg_.level_ptr = d_level_ptr_.p; sg_.row_base = d_row_base_.p;
-        sg_.row_stride = d_row_stride_.p; sg_.row_deg = d_row_deg_.p; sg_.ell_col = d_ell_col_.p; sg_.ell_size = ell_size_;
+        sg_.n = g_.n; sg_.m = g_.m; sg_.num_levels = num_levels_; sg_.level_ptr = d_level_ptr_.p;
+        sg_.row_deg = d_row_deg_.p; sg_.ell_col = d_ell_col_.p; sg_.ell_size = ell_size_;
+        sg_.level_ell = d_level_ell_.p; sg_.level_deg = d_level_deg_.p;
         return true;
     }
 
@@ -565,7 +569,7 @@ private:
     int num_levels_ = 0;
     bool use_smem_layered_ = false;
     std::vector<int> h_level_ptr_, h_level_rows_;
-    DevBuf<int> d_row_base_, d_row_stride_, d_row_deg_, d_ell_col_;
+    DevBuf<int> d_row_deg_, d_ell_col_, d_level_ell_, d_level_deg_;
     LayeredSmemGraph sg_{};
     size_t ell_size_ = 1;
     int smem_threads_ = 256;

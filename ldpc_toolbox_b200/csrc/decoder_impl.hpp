@@ -106,9 +106,9 @@ int generic_max_row_degree();
 struct LayeredSmemGraph {
     int n, m, num_levels;
     const int* level_ptr;    // num_levels+1, into the level-ordered row arrays below
-    const int* row_base;     // m: ELL index of slot 0 of the row
-    const int* row_stride;   // m: rows in the row's level (distance between slots)
-    const int* row_deg;      // m
+    const int* level_ell;    // num_levels: ELL index of the level's block
+    const int* level_deg;    // num_levels: the common degree of the level's rows, or -1 if they differ
+    const int* row_deg;      // m (level order): degree of each row; slot j of row i of level l is at level_ell[l] + j*rows(l) + i
     const int* ell_col;      // ell_size: variable of each slot (padding slots are never read)
     size_t ell_size;
 };

@@ -134,11 +134,16 @@ __global__ void __launch_bounds__(kSmemLayeredMaxThreads, 2) layered_smem_kernel
     // syndrome of the hard decisions given by hard_of(column): any unsatisfied row?
     auto unsatisfied = [&](auto hard_of) {
         uint32_t bad = 0;
-        for (int r = tid; r < g.m; r += T) {
-            const int base = __ldg(g.row_base + r), stride = __ldg(g.row_stride + r), d = __ldg(g.row_deg + r);
-            uint32_t par = 0;
-            for (int j = 0; j < d; ++j) par ^= hard_of(__ldg(g.ell_col + base + (size_t)j * stride));
-            bad |= par;
+        for (int l = 0; l < g.num_levels; ++l) {
+            const int r0 = __ldg(g.level_ptr + l), r1 = __ldg(g.level_ptr + l + 1), stride = r1 - r0;
+            const int off = __ldg(g.level_ell + l), ldeg = __ldg(g.level_deg + l);
+            for (int r = r0 + tid; r < r1; r += T) {
+                const int d = ldeg >= 0 ? ldeg : __ldg(g.row_deg + r);
+                const int* cc = g.ell_col + off + (r - r0);
+                uint32_t par = 0;
+                for (int j = 0; j < d; ++j) par ^= hard_of(__ldg(cc + (size_t)j * stride));
+                bad |= par;
+            }
         }
         return __syncthreads_or((int)bad) != 0;
     };
@@ -155,11 +160,13 @@ __global__ void __launch_bounds__(kSmemLayeredMaxThreads, 2) layered_smem_kernel
         for (int it = 1; it <= p.max_iter; ++it) {
             const bool first = it == 1;
             for (int l = 0; l < g.num_levels; ++l) {                               // horizontal_layered.rs:105-110
-                const int r0 = __ldg(g.level_ptr + l), r1 = __ldg(g.level_ptr + l + 1);
+                // per-level scalars (same for every thread, L1 hits): a row's loads then depend on nothing else
+                const int r0 = __ldg(g.level_ptr + l), r1 = __ldg(g.level_ptr + l + 1), stride = r1 - r0;
+                const int off = __ldg(g.level_ell + l), ldeg = __ldg(g.level_deg + l);
                 for (int r = r0 + tid; r < r1; r += T) {
-                    const int base = __ldg(g.row_base + r), stride = __ldg(g.row_stride + r), d = __ldg(g.row_deg + r);
-                    R* rr = rcv + base;
-                    const int* cc = g.ell_col + base;
+                    const int d = ldeg >= 0 ? ldeg : __ldg(g.row_deg + r);       // quasi-cyclic codes: one degree per level
+                    R* rr = rcv + off + (r - r0);
+                    const int* cc = g.ell_col + off + (r - r0);
                     // O(d) rules unroll up to degree 20 (5G-NR base graph 1: rows of degree 19), the O(d^2) ones to 10
                     constexpr int kUnrollMax = (RULE == kMinstarapprox || RULE == kTanh || sizeof(F) == 8) ? 10 : 20;
 #define LDPC_ROW_CASE(D_) case D_: process_row<F, RULE, IS_I8, HLIM, (D_ <= kUnrollMax ? D_ : 0), Q, R>(qs, rr, cc, stride, d, first, tb); break;
