@@ -334,8 +334,8 @@ private:
         }
         if (off > 0x7fffffffu) { set_last_error("level schedule too large"); return false; }
         ell_size_ = std::max<size_t>(off, 1);
-        smem_threads_ = std::min(256, std::max(64, (widest + 31) / 32 * 32));      // layered_smem_impl.cuh: at most 256
-        if (const char* e = getenv("LDPC_B200_K3Q_THREADS")) smem_threads_ = std::min(256, std::max(32, atoi(e) / 32 * 32));
+        smem_threads_ = std::min(kSmemLayeredMaxThreads, std::max(64, (widest + 31) / 32 * 32));
+        if (const char* e = getenv("LDPC_B200_K3Q_THREADS")) smem_threads_ = std::min(kSmemLayeredMaxThreads, std::max(32, atoi(e) / 32 * 32));
         if (!d_row_deg_.upload(row_deg) || !d_ell_col_.upload(ell_col) || !d_level_ell_.upload(level_ell) || !d_level_deg_.upload(level_deg))
             return false;
         sg_.n = g_.n; sg_.m = g_.m; sg_.num_levels = num_levels_; sg_.level_ptr = d_level_ptr_.p;

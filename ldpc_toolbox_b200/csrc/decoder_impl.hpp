@@ -103,6 +103,14 @@ int generic_max_row_degree();
 // Level schedule in ELL order (host-built once per code): rows are listed level by level; the slots
 // of a level form a block [max degree of the level][rows of the level], so slot j of consecutive
 // rows of a level is contiguous.  Rcv of a frame uses the same indexing.
+#ifndef LDPC_K3Q_MAX_THREADS
+#define LDPC_K3Q_MAX_THREADS 384
+#endif
+// CTA size bound of K3q.  384 threads x 2 CTAs per SM (80 registers, a few spills) beat 256 x 2 at 107
+// registers by 15-25 % on 5G-NR Z=384: the kernel is latency-bound, and 384 threads take exactly one row
+// each of a 384-row level (256 leave half the CTA idle in the second round).
+constexpr int kSmemLayeredMaxThreads = LDPC_K3Q_MAX_THREADS;
+
 struct LayeredSmemGraph {
     int n, m, num_levels;
     const int* level_ptr;    // num_levels+1, into the level-ordered row arrays below

@@ -92,12 +92,11 @@ __device__ __forceinline__ void process_row(Q* __restrict__ qs, R* __restrict__ 
     }
 }
 
-// 256 threads and two CTAs (frames) per SM: the second frame fills the level barriers and the Rcv
-// latency of the first (ncu, 512 threads x 1 CTA: 1.8 warps per issue stalled on the barrier, 2.8 on loads)
-constexpr int kSmemLayeredMaxThreads = 256;
-
+// Two CTAs (frames) per SM for the 4-byte and int8 arithmetics: the second frame fills the level barriers and
+// the load latency of the first (ncu at 512 threads x 1 CTA: 1.8 warps per issue stalled on the barrier, 2.8
+// on loads).  f64 posteriors leave room for one CTA only.
 template <class F, int RULE, bool IS_I8, bool HLIM>
-__global__ void __launch_bounds__(kSmemLayeredMaxThreads, 2) layered_smem_kernel(SmemLayeredParams<typename std::conditional<IS_I8, int16_t, F>::type,
+__global__ void __launch_bounds__(kSmemLayeredMaxThreads, sizeof(F) == 8 ? 1 : 2) layered_smem_kernel(SmemLayeredParams<typename std::conditional<IS_I8, int16_t, F>::type,
                                                       typename std::conditional<IS_I8, int8_t, F>::type> p) {
     using Q = typename std::conditional<IS_I8, int16_t, F>::type;
     using R = typename std::conditional<IS_I8, int8_t, F>::type;
