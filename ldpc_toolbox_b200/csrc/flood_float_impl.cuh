@@ -1,24 +1,17 @@
-// ldpc_toolbox_b200/csrc/flood_float_impl.cuh (K2), layered_tile_impl.cuh (K3) — K2 (flooding, float rules) and K3 (horizontal layered, all
-// rules): correctness-first kernels for the 20 implementations that are not the packed int8
-// flooding path (flood_i8.cu).
+// ldpc_toolbox_b200/csrc/flood_float_impl.cuh — K2: flooding-schedule BP with the float rules, one
+// thread-block cluster per 128-frame tile.
 //
-//   K2 replaces flooding::Decoder<A>::decode for A in {Phi, Tanh, Minstarapprox, Aminstar} x {f64, f32}
-//      reference src/decoder/flooding.rs:51-125, src/decoder/arithmetic.rs:140-156 (variable node)
-//   K3 replaces horizontal_layered::Decoder<A>::decode for the 12 HL* implementations
-//      reference src/decoder/horizontal_layered.rs:49-110 and the update_check_messages_and_vars
-//      methods of src/decoder/arithmetic.rs (:260-292, :393-426, :535-574, :759-801, :1013-1066,
-//      :1197-1257)
+//   replaces flooding::Decoder<A>::decode for A in {Phi, Tanh, Minstarapprox, Aminstar} x {f64, f32}
+//   reference src/decoder/flooding.rs:51-125, src/decoder/arithmetic.rs:140-156 (variable node),
+//   check rules in rules.cuh (arithmetic.rs:214-246, :347-379, :487-521, :942-999)
 //
 // Layout: 128-frame tiles, frame index fastest ([node][128] values); a lane owns 4 consecutive
 // frames and runs the reference's per-frame arithmetic on them one after the other, in the
-// reference's order.  One CTA owns a tile for the whole decode.
-//
-// The layered schedule is sequential over rows inside a frame.  Rows whose column supports are
-// disjoint commute exactly, so the host builds a level schedule (a row's level is one more than the
-// highest level of any earlier row sharing a column with it); rows of one level run on different
-// warps, levels are separated by a CTA barrier, and the result is identical to the reference's
-// row order 0..m-1.  (5G-NR: 384 rows per level; DVB-S2: the staircase chains every row to the
-// next, so its layered decoders run one row at a time.)
+// reference's order (sum order, product order, first argmin).  Messages live in one array in
+// row-major edge order, overwritten in place by each pass, like K1 (flood_i8.cu); hard decisions
+// are kept per edge so the syndrome of iteration i is read during the check pass of iteration i+1.
+// The CTAs of the tile's cluster split every pass (see flood_float_kernel).
+// Included by one translation unit per float type (flood_float_f32.cu, flood_float_f64.cu).
 #pragma once
 #include "bp_common.cuh"
 

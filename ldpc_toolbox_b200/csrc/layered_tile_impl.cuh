@@ -1,5 +1,17 @@
 // ldpc_toolbox_b200/csrc/layered_tile_impl.cuh — K3: horizontal-layered decoding on frame-interleaved
-// 128-frame tiles (see flood_float_impl.cuh for the file-level description and reference citations).
+// 128-frame tiles; the fallback for codes layered_smem_impl.cuh (K3q) does not take.
+//
+//   replaces horizontal_layered::Decoder<A>::decode for the 12 HL* implementations
+//   reference src/decoder/horizontal_layered.rs:49-110 and the update_check_messages_and_vars methods of
+//   src/decoder/arithmetic.rs (:260-292, :393-426, :535-574, :759-801, :1013-1066, :1197-1257)
+//
+// The layered schedule is sequential over rows inside a frame.  Rows whose column supports are
+// disjoint commute exactly, so the host builds a level schedule (a row's level is one more than the
+// highest level of any earlier row sharing a column with it); rows of one level run on different
+// warps, levels are separated by a CTA barrier, and the result is identical to the reference's
+// row order 0..m-1.  (DVB-S2: the staircase chains every row to the next, so its layered decoders
+// run one row at a time, 128 frames wide.)
+// Included by one translation unit per arithmetic type (layered_tile_f32.cu, _f64.cu, _i8.cu).
 #pragma once
 #include "bp_common.cuh"
 
