@@ -44,7 +44,7 @@ def measured_traffic(total_iterations: int):
     """DRAM bytes of one launch of the dominant kernel from the committed ncu capture
     (dram__bytes_read.sum + dram__bytes_write.sum), scaled by frame-iterations when the launch differs."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_d_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_e_traffic.json")))
         return (t["dram_bytes_read"] + t["dram_bytes_write"]) * total_iterations / (t["frames"] * t["iterations"])
     except Exception:
         return None
