@@ -2,9 +2,9 @@
 """Frame-level parity at scale for the float decoders (BASELINE.json: decoded words must match the
 reference's on >= 99.99 % of frames): decodes the same AWGN frames with the GPU path (C-ABI) and with
 the CPU checker (oracle/, all host threads) and counts frames whose hard word or iteration count differ.
-This is a test tool: the oracle is only the checker here.
+Test infrastructure (lives under tests/ because it loads the oracle): the oracle is only the checker here.
 
-  python tools/parity_scale.py --code nr5g:2:384 --impl HLMinstarapproxf32 --frames 8192 --ebn0 0.25 --max-iter 50
+  python tests/parity_scale.py --code nr5g:2:384 --impl HLMinstarapproxf32 --frames 8192 --ebn0 0.25 --max-iter 50
 """
 import argparse
 import json
@@ -16,7 +16,7 @@ import numpy as np
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import helpers  # noqa: E402
 import oraclelib  # noqa: E402
 from ldpc_toolbox_b200 import Decoder, codes  # noqa: E402
