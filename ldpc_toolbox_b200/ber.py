@@ -179,17 +179,28 @@ class BerTest:
                 raise e
         total = np.sum(parts, axis=0).astype(np.uint64)
         if self.allreduce is not None:
-            total = self.allreduce(total)
+            # The stop decision must be collective: besides the nine counters, rank 0's clock travels in
+            # the same all-reduce, so every rank applies ber.rs:522-531 to identical numbers and leaves
+            # the loop on the same round (the reference has one clock, in the controlling thread).
+            ext = np.zeros(NUM_COUNTERS + 1, dtype=np.uint64)
+            ext[:NUM_COUNTERS] = total
+            if self.rank == 0:
+                ext[NUM_COUNTERS] = np.uint64(max(0.0, time.perf_counter() - self._start) * 1e6)
+            ext = self.allreduce(ext)
+            total = ext[:NUM_COUNTERS].astype(np.uint64)
+            self._shared_elapsed = float(ext[NUM_COUNTERS]) * 1e-6
         return total
 
     def run(self) -> list[Statistics]:
         has_bch = self.bch_max_errors > 0
         for ebn0_db in self.ebn0s_db:
             counters = np.zeros(NUM_COUNTERS, dtype=np.uint64)
-            start = time.perf_counter()
+            start = self._start = time.perf_counter()
+            self._shared_elapsed = 0.0
             launch = 0
             while True:
-                elapsed = time.perf_counter() - start
+                # multi-rank: rank 0's clock as of the last all-reduce; single process: the local clock
+                elapsed = self._shared_elapsed if self.allreduce is not None else time.perf_counter() - start
                 errors = int(counters[7] if has_bch else counters[2])        # ber.rs:514-520
                 if run_finished(errors, self.max_frame_errors, elapsed, self.min_time, self.max_time):
                     break

@@ -22,6 +22,17 @@ const std::string& last_error() { return g_last_error; }
 
 namespace {
 
+// makes the decoder's GPU current for a call and restores the caller's device afterwards
+struct DeviceScope {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceScope(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -95,6 +106,11 @@ public:
             set_last_error("row degree above the supported maximum of " + std::to_string(max_deg));
             return false;
         }
+        // the packed variable node of K1 sums biased bytes in 16-bit halves: 255*(d+1) must stay below 2^15
+        if (kind_ == Kind::FloodI8 && g_.max_col_deg > 126) {
+            set_last_error("column degree above the supported maximum of 126 for the int8 flooding decoders");
+            return false;
+        }
         if (!d_row_ptr_.upload(g_.row_ptr) || !d_col_idx_.upload(g_.col_idx) || !d_col_ptr_.upload(g_.col_ptr) ||
             !d_col_edge_.upload(g_.col_edge))
             return false;
@@ -142,7 +158,8 @@ public:
                       uint8_t* out, size_t out_len, size_t out_stride, int32_t* iterations) override {
         if (!check_args(llrs_len, out_len, out_stride)) return false;
         if (nframes == 0) return true;
-        LDPC_CUDA_CHECK(cudaSetDevice(device_));
+        DeviceScope scope(device_);
+        if (!scope.ok) { set_last_error("cudaSetDevice failed"); return false; }
         const size_t esz = is_f64 ? 8 : 4;
         // Chunks are pipelined: the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the
         // kernels of chunk i (two staging buffers each way, copy engines on their own streams).
@@ -196,7 +213,8 @@ public:
                              cudaStream_t stream) override {
         if (!check_args(llrs_len, out_len, out_stride)) return false;
         if (nframes == 0) return true;
-        LDPC_CUDA_CHECK(cudaSetDevice(device_));
+        DeviceScope scope(device_);
+        if (!scope.ok) { set_last_error("cudaSetDevice failed"); return false; }
         const size_t esz = is_f64 ? 8 : 4;
         const size_t chunk_frames = plan_chunk_frames(nframes, 0);
         for (size_t f0 = 0; f0 < nframes; f0 += chunk_frames) {

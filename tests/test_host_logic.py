@@ -184,6 +184,48 @@ def test_ber_driver_world_size_2_gloo():
     assert (frames, fe, be, iters) == (single.num_frames, single.ldpc.frame_errors, single.ldpc.bit_errors, single.total_iterations)
 
 
+def _gloo_worker_max_time(rank, world, port, q):
+    import time
+
+    import torch
+    import torch.distributed as dist
+    from ldpc_toolbox_b200.ber import BerTest
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+    def allreduce(c):
+        t = torch.from_numpy(c.astype(np.int64))
+        dist.all_reduce(t)
+        return t.numpy().astype(np.uint64)
+
+    class SlowEngine(FakeEngine):
+        def run(self, *a):
+            time.sleep(0.002 if rank == 0 else 0.03)       # skewed local clocks: rank 1 is 15x slower per call
+            return super().run(*a)
+
+    if rank == 1:
+        time.sleep(0.2)                                    # and its clock starts late
+    t = BerTest([SlowEngine()], k=10, ebn0s_db=[1.0, 2.0], max_iterations=5, max_frame_errors=10**9, batch=64, rank=rank, world=world,
+                allreduce=allreduce, min_time=0.0, max_time=0.4)
+    st = t.run()
+    q.put((rank, [s.num_frames for s in st], [s.ldpc.frame_errors for s in st]))
+    dist.destroy_process_group()
+
+
+def test_ber_driver_world_size_2_gloo_time_limited():
+    """with --max-time the stop decision must be collective (rank 0's clock travels in the
+    all-reduce); per-rank clocks would let one rank leave the loop while the other enters the collective."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker_max_time, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    assert res[0][1:] == res[1][1:]
+    assert all(f > 0 and f % 128 == 0 for f in res[0][1])
+
+
 def test_systematic_reference_kat():
     """reference src/systematic.rs:99-121 (to_systematic), through alist text."""
     from ldpc_toolbox_b200 import cli, codes
