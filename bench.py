@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""bench.py — headline benchmark of the hot path (BASELINE.json config 3).
+"""bench.py — headline benchmark of the hot path (BASELINE.json configs[2]).
 
 Workload: DVB-S2 normal FECFRAME n=64800 r=1/2, decoder Minstarapproxi8 (flooding), 25 iterations,
 BPSK/AWGN at Eb/N0 = 0.5 dB (below threshold => every frame runs all 25 iterations: fixed work).
@@ -10,6 +10,13 @@ decoded information Gbit/s = k * frames / time (reference src/simulation/ber.rs:
   python bench.py --impl reference ...                          CPU arm: the C++ restatement of the
         reference's CPU path (the Rust crate cannot be built here), all host threads.
 
+Besides `value` (device-timed, LLRs resident in HBM) the line carries
+  e2e        the same metric through the host-buffer C-ABI (submit/wait over a ring of pinned buffers,
+             H2D and D2H inside the timed region), a fixed 8 half-launch batches per step at every N;
+  waterfall  the device-timed figure at the FER ~ 1e-2 point (SURVEY.md §8d (ii)) with average iterations;
+  parity     frames the CPU checker decoded (cpu_baseline's sample + a waterfall sample) pushed through the
+             kernel shape timed here (512-frame tiles, one CTA per tile) and compared word by word;
+  roofline / cpu_baseline   as the task contract defines them.
 Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
@@ -31,8 +38,16 @@ CODE = "dvbs2:R1_2"
 IMPL = "Minstarapproxi8"
 MAX_ITER = 25
 EBN0_DB = 0.5
+WATERFALL_DB = 1.2           # FER ~ 2e-2, 23.3 iterations on average (profiles/r01_d_ber_cli_dvbs2_r12_minstarapproxi8.txt)
 N, K_INFO, E = 64800, 32400, 226799
 METRIC = "decoded info Gbit/s (DVB-S2 n=64800 r=1/2 Minstarapproxi8, 25 it)"
+WORKLOAD = ("BASELINE.json configs[2]: DVB-S2 normal n=64800 r=1/2, Minstarapproxi8 flooding, max_iter 25, "
+            f"BPSK/AWGN Eb/N0 {EBN0_DB} dB (fixed work: every frame runs 25 iterations)")
+TRAFFIC_FILE = os.path.join("profiles", "r02_traffic.json")
+# identical in both arms (the driver compares it): the workload, and how the GPU arm defeats L2 reuse between steps
+CONFIG = {"workload": WORKLOAD,
+          "l2": "GPU arm: inputs of a step (39.3 GB of LLRs and 34.4 GB of message state at 151 552 frames) exceed the 126 MB L2; "
+                "no flush needed"}
 
 
 def algorithmic_bytes(total_iterations: int, frames: int) -> float:
@@ -41,13 +56,15 @@ def algorithmic_bytes(total_iterations: int, frames: int) -> float:
 
 
 def measured_traffic(total_iterations: int):
-    """DRAM bytes of one launch of the dominant kernel from the committed ncu capture
-    (dram__bytes_read.sum + dram__bytes_write.sum), scaled by frame-iterations when the launch differs."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_e_traffic.json")))
-        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * total_iterations / (t["frames"] * t["iterations"])
-    except Exception:
-        return None
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture of the
+    same kernel and configuration (dram__bytes_read.sum + dram__bytes_write.sum), scaled by frame-iterations."""
+    for name in (TRAFFIC_FILE, os.path.join("profiles", "r01_e_traffic.json")):
+        try:
+            t = json.load(open(os.path.join(ROOT, name)))
+            return (t["dram_bytes_read"] + t["dram_bytes_write"]) * total_iterations / (t["frames"] * t["iterations"]), name
+        except Exception:
+            continue
+    return None, None
 
 
 def measured_hbm_peak():
@@ -100,27 +117,21 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-def synth_llrs_device(torch, dev, frames: int, seed: int, chunk: int = 4096):
-    """Random messages -> product's own systematic encoder (C-ABI) -> BPSK -> AWGN (torch.randn on
-    the device) -> f32 LLRs [frames][n] resident in HBM.  64 distinct codewords are cycled."""
-    from ldpc_toolbox_b200 import Encoder, codes
-    alist = codes.cached_alist_path(CODE)
-    enc = Encoder(alist)
-    rng = np.random.default_rng(seed)
-    ncw = 64
-    cws = np.stack([enc.encode(rng.integers(0, 2, K_INFO, dtype=np.uint8), N) for _ in range(ncw)])
-    sym = torch.from_numpy(np.where(cws == 1, 1.0, -1.0).astype(np.float32)).to(dev)      # bit0 -> -1, bit1 -> +1
-    rate = K_INFO / N
-    sigma = float(np.sqrt(0.5 / (rate * 10 ** (np.float32(EBN0_DB) / 10))))
-    g = torch.Generator(device=dev)
+def sigma_of(ebn0_db: float) -> float:
+    return float(np.sqrt(0.5 / ((K_INFO / N) * 10 ** (np.float32(ebn0_db) / 10))))
+
+
+def fill_llrs_device(torch, llrs, sym, ebn0_db: float, seed: int, chunk: int = 4096):
+    """BPSK + AWGN (torch.randn on the device) -> f32 LLRs [frames][n] in place; codewords are cycled."""
+    sigma = sigma_of(ebn0_db)
+    g = torch.Generator(device=llrs.device)
     g.manual_seed(seed)
-    llrs = torch.empty((frames, N), dtype=torch.float32, device=dev)
+    frames, ncw = llrs.shape[0], sym.shape[0]
     for f0 in range(0, frames, chunk):
         nf = min(chunk, frames - f0)
-        idx = (torch.arange(f0, f0 + nf, device=dev) % ncw)
-        y = sym[idx] + sigma * torch.randn((nf, N), generator=g, device=dev, dtype=torch.float32)
+        idx = (torch.arange(f0, f0 + nf, device=llrs.device) % ncw)
+        y = sym[idx] + sigma * torch.randn((nf, N), generator=g, device=llrs.device, dtype=torch.float32)
         llrs[f0:f0 + nf] = (-2.0 / sigma**2) * y
-    return llrs, alist, cws
 
 
 def run_ours(args):
@@ -137,12 +148,18 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from ldpc_toolbox_b200 import Decoder
+    from ldpc_toolbox_b200 import Decoder, Encoder, codes
 
     sm = torch.cuda.get_device_properties(dev).multi_processor_count
     tiles = args.tiles if args.tiles > 0 else sm * 8      # 2 CTAs of 512 frames per SM
     frames = tiles * 128
-    llrs, alist, cws = synth_llrs_device(torch, dev, frames, seed=0x5EED + rank)
+    alist = codes.cached_alist_path(CODE)
+    enc = Encoder(alist)
+    rng = np.random.default_rng(0x5EED + rank)
+    cws = np.stack([enc.encode(rng.integers(0, 2, K_INFO, dtype=np.uint8), N) for _ in range(64)])
+    sym = torch.from_numpy(np.where(cws == 1, 1.0, -1.0).astype(np.float32)).to(dev)      # bit0 -> -1, bit1 -> +1
+    llrs = torch.empty((frames, N), dtype=torch.float32, device=dev)
+    fill_llrs_device(torch, llrs, sym, EBN0_DB, seed=0x5EED + rank)
     dec = Decoder(alist, IMPL, device=local, max_tiles=tiles)
     out = torch.empty((frames, K_INFO), dtype=torch.uint8, device=dev)
     iters = torch.empty((frames,), dtype=torch.int32, device=dev)
@@ -152,66 +169,82 @@ def run_ours(args):
         dec.decode_batch_ptr(llrs.data_ptr(), False, N, frames, MAX_ITER, out.data_ptr(), K_INFO, K_INFO, iters.data_ptr(),
                              device=True, stream=stream.cuda_stream)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    def timed(nsteps):
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         bp = []
-        for _ in range(args.steps):
+        for _ in range(nsteps):
             step()
             bp.append(dec.last_timing()["decode_ms"])     # library events around the BP kernel, same stream
         e1.record(stream)
         torch.cuda.synchronize(dev)
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    # correctness of the timed work: info bits of the decoded frames vs what was sent
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, bp
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
+    with ClockSampler(local) as clocks:
+        ms_total, bp = timed(args.steps)
     it_host = iters.cpu().numpy()
     total_iters = int(np.where(it_host < 0, MAX_ITER, it_host).sum())
-    # dominant kernel: device time of the BP kernel alone (events recorded inside the library on
-    # the launching stream around the flood kernel of the last step)
     tm = dec.last_timing()
     bp_ms = float(np.mean(bp))
     peak, peak_src = measured_hbm_peak()
     alg = algorithmic_bytes(total_iters, frames)
     achieved = alg / (bp_ms * 1e-3) / 1e9
+    out_ref = out.cpu()                                   # device-path words of the timed batch, for the e2e leg
+    it_ref = torch.from_numpy(it_host)
 
-    # ---- e2e: same metric through the public host-buffer call, H2D + D2H inside the timed region
-    # two launch-sized chunks so the library can overlap H2D / kernels / D2H, if host RAM allows pinning them
-    e2e_frames = args.e2e_tiles * 128 if args.e2e_tiles > 0 else 2 * frames
-    try:
-        avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
-    except Exception:
-        avail = 0
-    # one process pins at most a quarter of the available host RAM (an 88 GB pin once got the process
-    # OOM-killed), and all ranks of the node together at most 40 % (they pin at the same time)
-    while e2e_frames > 128 and e2e_frames * (N * 4 + K_INFO) > min(0.25 * avail, 0.4 * avail / world):
-        e2e_frames //= 2
-    h_llrs = torch.empty((e2e_frames, N), dtype=torch.float32, pin_memory=True)
-    for f0 in range(0, e2e_frames, frames):
-        nf = min(frames, e2e_frames - f0)
-        h_llrs[f0:f0 + nf].copy_(llrs[:nf])
-    del llrs, out, iters                       # free HBM for the library's double-buffered staging
+    # ---- e2e ring: two pinned slots of half a launch each, filled with the timed batch's own LLRs
+    half = frames // 2
+    h_llrs = [torch.empty((half, N), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    h_out = [torch.zeros((half, K_INFO), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    h_it = [torch.zeros((half,), dtype=torch.int32, pin_memory=True) for _ in range(2)]
+    for s in range(2):
+        h_llrs[s].copy_(llrs[s * half:(s + 1) * half])
+    torch.cuda.synchronize(dev)
+
+    # ---- waterfall point: same batch size, FER ~ 1e-2, early termination active
+    fill_llrs_device(torch, llrs, sym, WATERFALL_DB, seed=0xFA11 + rank)
+    step()
+    wf_ms, _ = timed(2)
+    wf_it = iters.cpu().numpy()
+    sent = torch.from_numpy(cws[:, :K_INFO])
+    wf_fe = 0
+    for f0 in range(0, frames, 16384):
+        nf = min(16384, frames - f0)
+        wf_fe += int((out[f0:f0 + nf].cpu() != sent[(torch.arange(f0, f0 + nf) % cws.shape[0])]).any(dim=1).sum())
+    waterfall = {"ebn0_db": WATERFALL_DB, "value": round(K_INFO * frames * 2 * world / (wf_ms * 1e-3) / 1e9, 4), "unit": "Gbit/s",
+                 "avg_iterations": round(float(np.where(wf_it < 0, MAX_ITER, wf_it).mean()), 3), "fer": wf_fe / frames,
+                 "frames_per_gpu": frames, "ms_per_step": round(wf_ms / 2, 3)}
+
+    # ---- e2e: same metric through the host-buffer C-ABI, H2D + D2H inside the timed region.  A step is a fixed
+    # 8 submits of half a launch (= 4 GPU-filling launches), identical at every N; the library pipelines them.
+    del llrs, out, iters
     torch.cuda.empty_cache()
-    h_out = torch.empty((e2e_frames, K_INFO), dtype=torch.uint8, pin_memory=True)
-    h_it = torch.empty((e2e_frames,), dtype=torch.int32, pin_memory=True)
+    submits = args.e2e_submits
 
     def e2e_step():
-        dec.decode_batch_ptr(h_llrs.data_ptr(), False, N, e2e_frames, MAX_ITER, h_out.data_ptr(), K_INFO, K_INFO, h_it.data_ptr(),
-                             device=False)
+        t = -1
+        for i in range(submits):
+            s = i % 2
+            t = dec.submit_batch_ptr(h_llrs[s].data_ptr(), False, N, half, MAX_ITER, h_out[s].data_ptr(), K_INFO, K_INFO, h_it[s].data_ptr())
+        dec.wait(t)
 
     e2e_step()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 2))
+    t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
     e2e_s = time.perf_counter() - t0
@@ -219,54 +252,90 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    sent = torch.from_numpy(cws[:, :K_INFO])
-    idx = torch.arange(e2e_frames) % cws.shape[0]
-    bit_errors = int((h_out != sent[idx]).sum())
+    e2e_frames = submits * half
+    e2e_same = all(bool((h_out[s] == out_ref[s * half:(s + 1) * half]).all()) and bool((h_it[s] == it_ref[s * half:(s + 1) * half]).all())
+                   for s in range(2))
     e2e_gbps = K_INFO * e2e_frames * e2e_steps * world / e2e_s / 1e9
 
     value = K_INFO * frames * args.steps * world / (ms_total * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic(total_iters)
     line = {
         "metric": METRIC, "value": round(value, 4), "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+        "warmup": warm, "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "i8", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[2]: DVB-S2 normal n=64800 r=1/2, Minstarapproxi8 flooding, max_iter 25, "
-                               f"BPSK/AWGN Eb/N0 {EBN0_DB} dB (fixed work: avg iterations {total_iters / frames:.2f})",
-                   "frames_per_gpu_per_step": frames, "tiles_per_gpu": tiles,
-                   "l2": "inputs (%.1f GB LLRs + %.1f GB message state per step) exceed the 126 MB L2" % (frames * N * 4 / 1e9, frames * E / 1e9),
-                   "edge_msgs_per_s": round(2.0 * E * total_iters * world / (ms_total / args.steps * 1e-3), 1)},
+        "config": CONFIG,
+        "run": {"avg_iterations": round(total_iters / frames, 3), "frames_per_gpu_per_step": frames, "tiles_per_gpu": tiles,
+                "llr_gb_per_step": round(frames * N * 4 / 1e9, 1), "message_state_gb": round(frames * E / 1e9, 1),
+                "edge_msgs_per_s": round(2.0 * E * total_iters * world / (ms_total / args.steps * 1e-3), 1)},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": measured_traffic(total_iters), "kernel": "flood_i8_kernel", "kernel_ms": round(bp_ms, 3), "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": f"{traffic_src}: committed ncu --set full capture of this kernel and configuration, not measured in this run",
+                     "kernel": "flood_i8_kernel", "kernel_ms": round(bp_ms, 3), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg},
         "e2e": {"value": round(e2e_gbps, 4), "unit": "Gbit/s", "h2d_bytes_per_step": e2e_frames * N * 4,
-                "d2h_bytes_per_step": e2e_frames * (K_INFO + 4), "frames_per_step": e2e_frames, "info_bit_errors": bit_errors},
+                "d2h_bytes_per_step": e2e_frames * (K_INFO + 4), "frames_per_step": e2e_frames, "submits_per_step": submits,
+                "frames_per_submit": half, "steps": e2e_steps, "pinned_ring_slots": 2,
+                "identical_to_device_path": e2e_same},
+        "waterfall": waterfall,
         "gpu_launches": 3 * args.steps,
         "stage_ms_last_step": {k: round(v, 3) for k, v in tm.items() if k.endswith("_ms")},
         "clocks": clocks.summary(),
     }
     if rank == 0:
         if args.cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(sample_seconds=args.cpu_seconds)
+            base, sample = cpu_baseline(sample_seconds=args.cpu_seconds, keep=True)
+            line["cpu_baseline"] = base
+            line["cpu_baseline_faithful_send"] = cpu_baseline(sample_seconds=min(args.cpu_seconds, 6.0), linear_search=True)
+            line["parity"] = parity_check(sample, local)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def parity_check(sample, device: int):
+    """The frames the CPU checker decoded for cpu_baseline (0.5 dB) plus a waterfall sample go through the
+    kernel shape timed above — 512-frame tiles (NW = 4), one CTA per tile — and are compared word by word."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oraclelib
+    from ldpc_toolbox_b200 import Decoder, codes
+    alist_text, llrs, rout, rits = sample
+    o = oraclelib.load()
+    _, wl = _cpu_sample(768, seed=79, ebn0_db=1.25)
+    wout, wits = o.decoder(alist_text, IMPL).decode_batch(wl, MAX_ITER, out_len=K_INFO, nthreads=os.cpu_count() or 1)
+    llrs = np.concatenate([llrs, wl])
+    rout = np.concatenate([rout, wout])
+    rits = np.concatenate([rits, wits])
+    os.environ["LDPC_B200_NW"] = "4"
+    os.environ["LDPC_B200_CLUSTER"] = "1"
+    try:
+        dec = Decoder(codes.cached_alist_path(CODE), IMPL, device=device)
+        out, its = dec.decode_batch(llrs, MAX_ITER, output_len=K_INFO)
+        dec.close()
+    finally:
+        del os.environ["LDPC_B200_NW"], os.environ["LDPC_B200_CLUSTER"]
+    return {"checked_frames": int(llrs.shape[0]), "word_mismatches": int((out != rout).any(axis=1).sum()),
+            "iteration_mismatches": int((its != rits).sum()), "converged_frames": int((rits >= 0).sum()),
+            "kernel": "flood_i8_kernel<NW=4>, one CTA per 512-frame tile (the shape timed above)",
+            "checker": "oracle/ C++ restatement of the reference (bit-exact contract: words and iteration counts)"}
+
+
 # ----------------------------------------------------------------------------------------------
-def _cpu_sample(nframes: int, seed: int):
-    """Same workload on the host: LLR frames for the oracle (numpy)."""
-    from ldpc_toolbox_b200 import Encoder, codes
-    alist_path = codes.cached_alist_path(CODE)
-    enc = Encoder(alist_path)
+def _cpu_sample(nframes: int, seed: int, ebn0_db: float = EBN0_DB):
+    """Same workload on the host, built with the checker's own encoder (no product code): alist text and f32 LLRs."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oraclelib
+    from ldpc_toolbox_b200 import codes          # pure-Python alist generator (standards tables), no CUDA library
+    alist_text = open(codes.cached_alist_path(CODE)).read()
+    enc = oraclelib.load().encoder(alist_text)
     rng = np.random.default_rng(seed)
     cws = np.stack([enc.encode(rng.integers(0, 2, K_INFO, dtype=np.uint8), N) for _ in range(min(nframes, 16))])
-    sigma = float(np.sqrt(0.5 / ((K_INFO / N) * 10 ** (np.float32(EBN0_DB) / 10))))
+    sigma = sigma_of(ebn0_db)
     sym = np.where(cws == 1, 1.0, -1.0).astype(np.float32)[np.arange(nframes) % cws.shape[0]]
     y = sym + sigma * rng.standard_normal(sym.shape, dtype=np.float32)
-    return open(alist_path).read(), (-2.0 / sigma**2 * y).astype(np.float32)
+    return alist_text, (-2.0 / sigma**2 * y).astype(np.float32)
 
 
-def cpu_baseline(sample_seconds: float = 15.0, linear_search: bool = False):
+def cpu_baseline(sample_seconds: float = 15.0, linear_search: bool = False, keep: bool = False):
     """The CPU restatement of the reference's path (oracle/, "port") on all host cores, on a
     bounded sample of the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -283,13 +352,14 @@ def cpu_baseline(sample_seconds: float = 15.0, linear_search: bool = False):
     nframes -= nframes % cores
     alist, llrs = _cpu_sample(nframes, seed=78)
     t0 = time.perf_counter()
-    _, its = dec.decode_batch(llrs, MAX_ITER, out_len=K_INFO, nthreads=cores)
+    out, its = dec.decode_batch(llrs, MAX_ITER, out_len=K_INFO, nthreads=cores)
     el = time.perf_counter() - t0
-    return {"value": round(K_INFO * nframes / el / 1e9, 6), "unit": "Gbit/s", "cores": cores, "kind": "port",
-            "sample": f"{nframes} frames of the same workload in {el:.1f} s, C++ restatement of the reference CPU path "
-                      f"(Rust toolchain unavailable), {'linear-search send' if linear_search else 'direct edge indexing'}, "
-                      f"avg iterations {float(np.where(its < 0, MAX_ITER, its).mean()):.2f}",
-            "frames_per_s": round(nframes / el, 2)}
+    res = {"value": round(K_INFO * nframes / el / 1e9, 6), "unit": "Gbit/s", "cores": cores, "kind": "port",
+           "sample": f"{nframes} frames of the same workload in {el:.1f} s, C++ restatement of the reference CPU path "
+                     f"(Rust toolchain unavailable), {'linear-search send as in src/decoder.rs:111-117' if linear_search else 'direct edge indexing'}, "
+                     f"avg iterations {float(np.where(its < 0, MAX_ITER, its).mean()):.2f}",
+           "frames_per_s": round(nframes / el, 2)}
+    return (res, (alist, llrs, out, its)) if keep else res
 
 
 def run_reference(args):
@@ -297,10 +367,9 @@ def run_reference(args):
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    vals, samples = [], []
+    vals = []
     for _ in range(args.warmup + args.steps):
-        b = cpu_baseline(sample_seconds=min(args.cpu_seconds, 10.0), linear_search=args.faithful_send)
-        vals.append(b)
+        vals.append(cpu_baseline(sample_seconds=min(args.cpu_seconds, 10.0), linear_search=args.faithful_send))
     timed = vals[args.warmup:] or vals
     v = float(np.mean([b["value"] for b in timed]))
     fps = float(np.mean([b["frames_per_s"] for b in timed]))
@@ -308,8 +377,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": round(v, 6), "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 * K_INFO * 1 / max(v * 1e9, 1e-9), 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "i8", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[2]: DVB-S2 normal n=64800 r=1/2, Minstarapproxi8 flooding, max_iter 25, "
-                               f"BPSK/AWGN Eb/N0 {EBN0_DB} dB", "frames_per_s": fps},
+        "config": CONFIG,
+        "run": {"frames_per_s": fps},
         "cpu_baseline": dict(timed[-1], value=round(v, 6)),
         "e2e": {"value": round(v, 6), "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -324,7 +393,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tiles", type=int, default=0, help="frames per GPU per step / 128 (default 8 per SM = two 512-frame tiles per SM)")
-    ap.add_argument("--e2e-tiles", type=int, default=0, help="frames of the end-to-end leg / 128 (default: two launches' worth)")
+    ap.add_argument("--e2e-submits", type=int, default=8, help="half-launch batches submitted per end-to-end step")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--faithful-send", action="store_true", help="reference arm: time the linear-search send of decoder.rs:111-117")

@@ -83,7 +83,29 @@ int32_t ldpc_toolbox_decoder_decode_batch_f64(void *decoder, uint8_t *output, si
                                               size_t output_stride, const double *llrs,
                                               size_t llrs_len, size_t nframes,
                                               uint32_t max_iterations, int32_t *iterations);
-/* Same, with every buffer in device memory of the decoder's GPU; asynchronous on `cuda_stream`
+/* Asynchronous form of the batched decode, for streaming callers: submit returns a ticket (>= 0) as soon
+ * as the copies and kernels are enqueued (-2 on an argument / CUDA error) and wait(ticket) blocks until
+ * that batch — and every batch submitted before it — has been written to `output` / `iterations`.  The
+ * library pipelines H2D copies, decoding and D2H copies across consecutive submits, so a caller that keeps
+ * two batches in flight never exposes a copy.  All buffers of a submit must stay valid until its wait
+ * returns, and must be pinned (cudaHostAlloc / cudaHostRegister) for the call not to block.
+ * decode_batch_* is submit + wait. */
+int64_t ldpc_toolbox_decoder_submit_batch_f32(void *decoder, uint8_t *output, size_t output_len,
+                                              size_t output_stride, const float *llrs,
+                                              size_t llrs_len, size_t nframes,
+                                              uint32_t max_iterations, int32_t *iterations);
+int64_t ldpc_toolbox_decoder_submit_batch_f64(void *decoder, uint8_t *output, size_t output_len,
+                                              size_t output_stride, const double *llrs,
+                                              size_t llrs_len, size_t nframes,
+                                              uint32_t max_iterations, int32_t *iterations);
+int32_t ldpc_toolbox_decoder_wait(void *decoder, int64_t ticket);
+
+/* One handle = one caller: like the reference's `&mut` handle (src/c_api/decoder.rs:120) a decoder must not be
+ * used from two threads at once, and the device-pointer calls below share one workspace per handle — calls
+ * on the same handle must be issued on ONE stream (use one handle per stream).  Every entry point restores
+ * the caller's current CUDA device before returning.
+ *
+ * Same, with every buffer in device memory of the decoder's GPU; asynchronous on `cuda_stream`
  * (a cudaStream_t; NULL = the legacy default stream). */
 int32_t ldpc_toolbox_decoder_decode_batch_device_f32(void *decoder, uint8_t *d_output,
                                                      size_t output_len, size_t output_stride,
@@ -95,6 +117,19 @@ int32_t ldpc_toolbox_decoder_decode_batch_device_f64(void *decoder, uint8_t *d_o
                                                      const double *d_llrs, size_t llrs_len,
                                                      size_t nframes, uint32_t max_iterations,
                                                      int32_t *d_iterations, void *cuda_stream);
+
+/* Test hook for the float decoders (flooding and frame-per-CTA layered kernels): batched decode that also returns
+ * every frame's posterior LLRs as f64 [nframes][n] — the flooding decoder's output_llrs (reference
+ * src/decoder/flooding.rs:111-125) / the layered decoder's Qv (src/decoder/horizontal_layered.rs:65-88) when the
+ * frame stopped.  Frames with 0 iterations have none (zeros).  One chunk only; -2 on error. */
+int32_t ldpc_toolbox_decoder_decode_batch_posteriors_f32(void *decoder, uint8_t *output, size_t output_len,
+                                                         size_t output_stride, const float *llrs, size_t llrs_len,
+                                                         size_t nframes, uint32_t max_iterations,
+                                                         int32_t *iterations, double *posteriors);
+int32_t ldpc_toolbox_decoder_decode_batch_posteriors_f64(void *decoder, uint8_t *output, size_t output_len,
+                                                         size_t output_stride, const double *llrs, size_t llrs_len,
+                                                         size_t nframes, uint32_t max_iterations,
+                                                         int32_t *iterations, double *posteriors);
 
 /* Introspection */
 size_t ldpc_toolbox_decoder_codeword_len(void *decoder);   /* n (columns of H) */

@@ -16,6 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libldpc_toolbox.so")
+STATIC_LIB = os.path.join(OUT_DIR, "libldpc_toolbox.a")     # the reference builds cdylib + staticlib (Cargo.toml:17-19)
 
 # heavy kernels first: one nvcc per translation unit runs in parallel (see build())
 CU_SOURCES = ["flood_float_f64.cu", "flood_float_f32.cu", "layered_smem_f64.cu", "layered_smem_f32.cu", "layered_tile_f64.cu",
@@ -59,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     stamp = os.path.join(OUT_DIR, "stamp.txt")
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+    if not force and os.path.exists(LIB) and os.path.exists(STATIC_LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     nvcc = _nvcc()
     objs = []
@@ -102,6 +103,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(log[-1])
         raise RuntimeError("link failed")
+    # static archive of the same objects (link with: g++ app.o libldpc_toolbox.a -lcudart)
+    if os.path.exists(STATIC_LIB):
+        os.remove(STATIC_LIB)
+    cmd = ["ar", "rcs", STATIC_LIB] + objs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        sys.stderr.write(log[-1])
+        raise RuntimeError("ar failed")
     open(os.path.join(OUT_DIR, "build.log"), "w").write("\n".join(log))
     open(stamp, "w").write(dig)
     if verbose:

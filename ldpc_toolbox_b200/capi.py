@@ -26,6 +26,11 @@ _SIGS = {
     "ldpc_toolbox_decoder_ctor_ex": (C.c_void_p, [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int]),
     "ldpc_toolbox_decoder_decode_batch_f32": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p]),
     "ldpc_toolbox_decoder_decode_batch_f64": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p]),
+    "ldpc_toolbox_decoder_submit_batch_f32": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p]),
+    "ldpc_toolbox_decoder_submit_batch_f64": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p]),
+    "ldpc_toolbox_decoder_decode_batch_posteriors_f32": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "ldpc_toolbox_decoder_decode_batch_posteriors_f64": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "ldpc_toolbox_decoder_wait": (C.c_int32, [C.c_void_p, C.c_int64]),
     "ldpc_toolbox_decoder_decode_batch_device_f32": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]),
     "ldpc_toolbox_decoder_decode_batch_device_f64": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]),
     "ldpc_toolbox_decoder_codeword_len": (C.c_size_t, [C.c_void_p]),

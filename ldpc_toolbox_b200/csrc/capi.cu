@@ -100,6 +100,15 @@ int32_t decode_batch(void* decoder, uint8_t* output, size_t output_len, size_t o
 }
 
 template <class T>
+int64_t submit_batch(void* decoder, uint8_t* output, size_t output_len, size_t output_stride, const T* llrs, size_t llrs_len,
+                     size_t nframes, uint32_t max_it, int32_t* iterations) {
+    if (!decoder || !iterations || !llrs || (!output && output_len)) return -2;
+    auto* h = static_cast<DecoderHandle*>(decoder);
+    const int64_t t = h->decoder->submit_batch(llrs, sizeof(T) == 8, llrs_len, nframes, max_it, output, output_len, output_stride, iterations);
+    return t >= 0 ? t : -2;
+}
+
+template <class T>
 int32_t decode_batch_device(void* decoder, uint8_t* d_output, size_t output_len, size_t output_stride, const T* d_llrs,
                             size_t llrs_len, size_t nframes, uint32_t max_it, int32_t* d_iterations, void* stream) {
     if (!decoder || !d_iterations || !d_llrs || (!d_output && output_len)) return -2;
@@ -157,6 +166,39 @@ int32_t ldpc_toolbox_decoder_decode_batch_f64(void* decoder, uint8_t* output, si
                                               const double* llrs, size_t llrs_len, size_t nframes, uint32_t max_iterations,
                                               int32_t* iterations) {
     return decode_batch(decoder, output, output_len, output_stride, llrs, llrs_len, nframes, max_iterations, iterations);
+}
+
+int64_t ldpc_toolbox_decoder_submit_batch_f32(void* decoder, uint8_t* output, size_t output_len, size_t output_stride,
+                                              const float* llrs, size_t llrs_len, size_t nframes, uint32_t max_iterations,
+                                              int32_t* iterations) {
+    return submit_batch(decoder, output, output_len, output_stride, llrs, llrs_len, nframes, max_iterations, iterations);
+}
+
+int64_t ldpc_toolbox_decoder_submit_batch_f64(void* decoder, uint8_t* output, size_t output_len, size_t output_stride,
+                                              const double* llrs, size_t llrs_len, size_t nframes, uint32_t max_iterations,
+                                              int32_t* iterations) {
+    return submit_batch(decoder, output, output_len, output_stride, llrs, llrs_len, nframes, max_iterations, iterations);
+}
+
+int32_t ldpc_toolbox_decoder_decode_batch_posteriors_f32(void* decoder, uint8_t* output, size_t output_len, size_t output_stride,
+                                                         const float* llrs, size_t llrs_len, size_t nframes, uint32_t max_iterations,
+                                                         int32_t* iterations, double* posteriors) {
+    if (!decoder || !iterations || !llrs || !posteriors || (!output && output_len)) return -2;
+    return static_cast<DecoderHandle*>(decoder)->decoder->decode_batch_posteriors(llrs, false, llrs_len, nframes, max_iterations, output,
+                                                                                  output_len, output_stride, iterations, posteriors) ? 0 : -2;
+}
+
+int32_t ldpc_toolbox_decoder_decode_batch_posteriors_f64(void* decoder, uint8_t* output, size_t output_len, size_t output_stride,
+                                                         const double* llrs, size_t llrs_len, size_t nframes, uint32_t max_iterations,
+                                                         int32_t* iterations, double* posteriors) {
+    if (!decoder || !iterations || !llrs || !posteriors || (!output && output_len)) return -2;
+    return static_cast<DecoderHandle*>(decoder)->decoder->decode_batch_posteriors(llrs, true, llrs_len, nframes, max_iterations, output,
+                                                                                  output_len, output_stride, iterations, posteriors) ? 0 : -2;
+}
+
+int32_t ldpc_toolbox_decoder_wait(void* decoder, int64_t ticket) {
+    if (!decoder || ticket < 0) return -2;
+    return static_cast<DecoderHandle*>(decoder)->decoder->wait(ticket) ? 0 : -2;
 }
 
 int32_t ldpc_toolbox_decoder_decode_batch_device_f32(void* decoder, uint8_t* d_output, size_t output_len, size_t output_stride,

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 
 #include "decoder_impl.hpp"
 #include "rules.cuh"
@@ -60,18 +61,38 @@ struct DevBuf {
     }
 };
 
+// per-launch decoder state in HBM; the host path keeps two of them so that two
+// launches can be resident at once
+struct Workspace {
+    DevBuf<uint8_t> msg, inq, hbit, hard, final_hard, cbit;
+    DevBuf<int32_t> iters_tile;
+    size_t bytes() const { return msg.count + inq.count + hbit.count + hard.count + final_hard.count + cbit.count; }
+};
+
+// one staging slot of the host path: H2D target, D2H source and the events that order their reuse
+struct StageSlot {
+    DevBuf<uint8_t> in, out;
+    DevBuf<int32_t> iters;
+    cudaEvent_t copied = nullptr, ingested = nullptr, emitted = nullptr, drained = nullptr;
+    bool used = false;
+};
+
 class GpuDecoder final : public LdpcDecoder {
 public:
     GpuDecoder(const DecoderImplementation& impl, const Graph& g) : impl_(impl), g_(g) {}
     ~GpuDecoder() override {
+        cudaSetDevice(device_);
+        cudaDeviceSynchronize();
         if (stream_) cudaStreamDestroy(stream_);
+        if (stream2_) cudaStreamDestroy(stream2_);
         if (h2d_stream_) cudaStreamDestroy(h2d_stream_);
         if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
         for (auto& e : ev_) if (e) cudaEventDestroy(e);
         if (ev_hist_) cudaEventDestroy(ev_hist_);
         if (h_hist_) cudaFreeHost(h_hist_);
-        for (int b = 0; b < 2; ++b)
-            for (cudaEvent_t e : {ev_copied_[b], ev_ingested_[b], ev_emitted_[b], ev_drained_[b]}) if (e) cudaEventDestroy(e);
+        for (auto& sl : slot_)
+            for (cudaEvent_t e : {sl.copied, sl.ingested, sl.emitted, sl.drained}) if (e) cudaEventDestroy(e);
+        for (auto& t : tickets_) if (t.done) cudaEventDestroy(t.done);
     }
 
     bool init(const Puncturer* punct, const DecoderOptions& opt) {
@@ -116,7 +137,7 @@ public:
             return false;
         dg_.n = g_.n; dg_.m = g_.m; dg_.E = g_.E;
         dg_.row_ptr = d_row_ptr_.p; dg_.col_idx = d_col_idx_.p; dg_.col_ptr = d_col_ptr_.p; dg_.col_edge = d_col_edge_.p;
-        if (kind_ == Kind::FloodI8 && !build_var_classes()) return false;
+        if (kind_ == Kind::FloodI8 && (!build_row_meta() || !build_var_classes())) return false;
         if (kind_ == Kind::Layered && !build_levels()) return false;
         if (kind_ == Kind::Layered) {
             // K3q (frame per CTA, posteriors in shared memory) when they fit and the level schedule is wide
@@ -156,54 +177,122 @@ public:
 
     bool decode_batch(const void* llrs, bool is_f64, size_t llrs_len, size_t nframes, uint32_t max_iterations,
                       uint8_t* out, size_t out_len, size_t out_stride, int32_t* iterations) override {
+        const int64_t t = submit_batch(llrs, is_f64, llrs_len, nframes, max_iterations, out, out_len, out_stride, iterations);
+        return t >= 0 && wait(t);
+    }
+
+    // Asynchronous host-buffer decode.  The batch is cut into chunks that flow through a three-stage
+    // pipeline — H2D copy (copy engine) -> ingest + BP + emit -> D2H copy — over two staging slots.  The int8
+    // flooding decoder on big batches uses chunks of HALF a GPU-filling launch on two compute streams with
+    // their own workspaces, so two launches are co-resident (one CTA per SM each): the exposed prologue is
+    // the copy of half a launch, a finishing launch is replaced while the other keeps the SMs busy, and
+    // consecutive submit_batch calls keep the pipeline full.  Nothing here blocks the host when the caller's
+    // buffers are pinned; wait(ticket) does.
+    int64_t submit_batch(const void* llrs, bool is_f64, size_t llrs_len, size_t nframes, uint32_t max_iterations,
+                         uint8_t* out, size_t out_len, size_t out_stride, int32_t* iterations) override {
+        if (!check_args(llrs_len, out_len, out_stride)) return -1;
+        DeviceScope scope(device_);
+        if (!scope.ok) { set_last_error("cudaSetDevice failed"); return -1; }
+        if (!ensure_pipeline()) return -1;
+        const int64_t ticket = next_ticket_++;
+        Ticket tk;
+        tk.id = ticket;
+        if (cudaEventCreateWithFlags(&tk.done, cudaEventDisableTiming) != cudaSuccess) { set_last_error("cudaEventCreate failed"); return -1; }
+        if (nframes > 0) {
+            const size_t esz = is_f64 ? 8 : 4;
+            int lanes = 1;
+            const size_t chunk_frames = plan_host_chunks(nframes, 2 * (llrs_len * esz + out_len + 4), &lanes);
+            // staging buffers only ever grow; growing them waits for everything in flight first
+            const size_t stage_frames = std::min(nframes, chunk_frames);
+            const size_t need_in = stage_frames * llrs_len * esz, need_out = std::max<size_t>(stage_frames * out_len, 1);
+            const size_t nchunks = (nframes + chunk_frames - 1) / chunk_frames;
+            for (int b = 0; b < (nchunks > 1 ? 2 : 1); ++b) {
+                StageSlot& sl = slot_[(slot_counter_ + (size_t)b) % 2];
+                if (sl.in.count < need_in || sl.out.count < need_out || sl.iters.count < stage_frames) {
+                    cudaDeviceSynchronize();
+                    if (!sl.in.ensure(need_in) || !sl.out.ensure(need_out) || !sl.iters.ensure(stage_frames)) { cudaEventDestroy(tk.done); return -1; }
+                }
+            }
+            for (size_t f0 = 0; f0 < nframes; f0 += chunk_frames) {
+                StageSlot& sl = slot_[slot_counter_ % 2];
+                const int w = lanes == 2 ? (int)(slot_counter_ % 2) : 0;
+                ++slot_counter_;
+                cudaStream_t cs = w == 0 ? stream_ : stream2_;
+                const size_t nf = std::min(chunk_frames, nframes - f0);
+                if (!enqueue_chunk(sl, ws_[w], cs, (const uint8_t*)llrs + f0 * llrs_len * esz, is_f64, llrs_len, nf, max_iterations,
+                                   out + f0 * out_stride, out_len, out_stride, iterations + f0)) {
+                    cudaEventDestroy(tk.done);
+                    return -1;
+                }
+            }
+        }
+        if (cudaEventRecord(tk.done, d2h_stream_) != cudaSuccess) { set_last_error("cudaEventRecord failed"); cudaEventDestroy(tk.done); return -1; }
+        tickets_.push_back(tk);
+        return ticket;
+    }
+
+    bool wait(int64_t ticket) override {
+        DeviceScope scope(device_);
+        bool ok = true;
+        // tickets complete in order (one D2H stream): waiting for one retires every older one too
+        while (!tickets_.empty() && tickets_.front().id <= ticket) {
+            Ticket tk = tickets_.front();
+            tickets_.pop_front();
+            cudaError_t e = cudaEventSynchronize(tk.done);
+            cudaEventDestroy(tk.done);
+            if (e != cudaSuccess) { set_last_error(std::string("decode failed: ") + cudaGetErrorString(e)); ok = false; }
+        }
+        if (tickets_.empty()) {
+            // surface asynchronous kernel errors of the compute streams as well
+            for (cudaStream_t st : {stream_, stream2_}) {
+                if (!st) continue;
+                cudaError_t e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) { set_last_error(std::string("decode failed: ") + cudaGetErrorString(e)); ok = false; }
+            }
+        }
+        return ok;
+    }
+
+    // Test hook: decode_batch on one chunk that also returns every frame's posterior LLRs as f64 [nframes][n] — the
+    // flooding decoder's output_llrs (flooding.rs:111-125) / the layered decoder's Qv — for the float decoders on the
+    // K2 and K3q kernels.  Frames that pass the pre-check (0 iterations) have no posteriors (the reference's are stale).
+    bool decode_batch_posteriors(const void* llrs, bool is_f64, size_t llrs_len, size_t nframes, uint32_t max_iterations,
+                                 uint8_t* out, size_t out_len, size_t out_stride, int32_t* iterations, double* posteriors) override {
         if (!check_args(llrs_len, out_len, out_stride)) return false;
+        if (kind_ == Kind::FloodI8 || impl_.dtype == Dtype::I8 || (kind_ == Kind::Layered && !use_smem_layered_)) {
+            set_last_error("posterior output is implemented for the float decoders on the flooding and frame-per-CTA layered kernels");
+            return false;
+        }
         if (nframes == 0) return true;
         DeviceScope scope(device_);
         if (!scope.ok) { set_last_error("cudaSetDevice failed"); return false; }
-        const size_t esz = is_f64 ? 8 : 4;
-        // Chunks are pipelined: the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the
-        // kernels of chunk i (two staging buffers each way, copy engines on their own streams).
-        // Truly asynchronous only when the caller's buffers are pinned.
-        size_t chunk_frames = plan_chunk_frames(nframes, /*staging_bytes_per_frame=*/2 * (llrs_len * esz + out_len + 4));
-        const size_t nchunks = (nframes + chunk_frames - 1) / chunk_frames;
-        const int nbuf = nchunks > 1 ? 2 : 1;
-        const size_t stage_frames = std::min(nframes, chunk_frames);
-        for (int b = 0; b < nbuf; ++b)
-            if (!d_stage_in_[b].ensure(stage_frames * llrs_len * esz) || !d_stage_out_[b].ensure(std::max<size_t>(stage_frames * out_len, 1)) ||
-                !d_stage_iters_[b].ensure(stage_frames))
-                return false;
-        if (!h2d_stream_) {
-            LDPC_CUDA_CHECK(cudaStreamCreateWithFlags(&h2d_stream_, cudaStreamNonBlocking));
-            LDPC_CUDA_CHECK(cudaStreamCreateWithFlags(&d2h_stream_, cudaStreamNonBlocking));
-            for (int b = 0; b < 2; ++b) {
-                LDPC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_copied_[b], cudaEventDisableTiming));
-                LDPC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_ingested_[b], cudaEventDisableTiming));
-                LDPC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_emitted_[b], cudaEventDisableTiming));
-                LDPC_CUDA_CHECK(cudaEventCreateWithFlags(&ev_drained_[b], cudaEventDisableTiming));
-            }
+        if (nframes > plan_chunk_frames(nframes, 0)) { set_last_error("too many frames for one chunk"); return false; }
+        const size_t esz = is_f64 ? 8 : 4, n = (size_t)g_.n;
+        DevBuf<uint8_t> d_in, d_out, d_post_tiles;
+        DevBuf<int32_t> d_it;
+        DevBuf<double> d_post;
+        const size_t tiles = (nframes + kTileFrames - 1) / kTileFrames;
+        if (!d_in.ensure(nframes * llrs_len * esz) || !d_out.ensure(std::max<size_t>(nframes * out_len, 1)) || !d_it.ensure(nframes) ||
+            !d_post.ensure(nframes * n))
+            return false;
+        LDPC_CUDA_CHECK(cudaMemsetAsync(d_post.p, 0, nframes * n * sizeof(double), stream_));
+        if (kind_ == Kind::FloodFloat) {
+            if (!d_post_tiles.ensure(tiles * n * kTileFrames * elem_size())) return false;
+            LDPC_CUDA_CHECK(cudaMemsetAsync(d_post_tiles.p, 0, tiles * n * kTileFrames * elem_size(), stream_));
+            dump_post_tiles_ = d_post_tiles.p;
+        } else {
+            dump_post_ = d_post.p;
         }
-        size_t ci = 0;
-        for (size_t f0 = 0; f0 < nframes; f0 += chunk_frames, ++ci) {
-            const int b = (int)(ci % (size_t)nbuf);
-            const size_t nf = std::min(chunk_frames, nframes - f0);
-            if (ci >= (size_t)nbuf) LDPC_CUDA_CHECK(cudaStreamWaitEvent(h2d_stream_, ev_ingested_[b], 0));   // staging-in buffer consumed
-            LDPC_CUDA_CHECK(cudaMemcpyAsync(d_stage_in_[b].p, (const uint8_t*)llrs + f0 * llrs_len * esz, nf * llrs_len * esz,
-                                            cudaMemcpyHostToDevice, h2d_stream_));
-            LDPC_CUDA_CHECK(cudaEventRecord(ev_copied_[b], h2d_stream_));
-            LDPC_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_copied_[b], 0));
-            if (ci >= (size_t)nbuf) LDPC_CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_drained_[b], 0));        // staging-out buffer drained
-            if (!run_chunk(d_stage_in_[b].p, is_f64, llrs_len, nf, max_iterations, d_stage_out_[b].p, out_len, out_len,
-                           d_stage_iters_[b].p, stream_, ev_ingested_[b]))
-                return false;
-            LDPC_CUDA_CHECK(cudaEventRecord(ev_emitted_[b], stream_));
-            LDPC_CUDA_CHECK(cudaStreamWaitEvent(d2h_stream_, ev_emitted_[b], 0));
-            if (out_len)
-                LDPC_CUDA_CHECK(cudaMemcpy2DAsync(out + f0 * out_stride, out_stride, d_stage_out_[b].p, out_len, out_len, nf,
-                                                  cudaMemcpyDeviceToHost, d2h_stream_));
-            LDPC_CUDA_CHECK(cudaMemcpyAsync(iterations + f0, d_stage_iters_[b].p, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, d2h_stream_));
-            LDPC_CUDA_CHECK(cudaEventRecord(ev_drained_[b], d2h_stream_));
-        }
-        LDPC_CUDA_CHECK(cudaStreamSynchronize(d2h_stream_));
+        LDPC_CUDA_CHECK(cudaMemcpyAsync(d_in.p, llrs, nframes * llrs_len * esz, cudaMemcpyHostToDevice, stream_));
+        const bool ok = run_chunk(ws_[0], d_in.p, is_f64, llrs_len, nframes, max_iterations, d_out.p, out_len, out_len, d_it.p, stream_);
+        void* tiles_ptr = dump_post_tiles_;
+        dump_post_tiles_ = nullptr;
+        dump_post_ = nullptr;
+        if (!ok) return false;
+        if (tiles_ptr && !launch_emit_posteriors(tiles_ptr, impl_.dtype == Dtype::F64, g_.n, nframes, d_post.p, stream_)) return false;
+        if (out_len) LDPC_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride, d_out.p, out_len, out_len, nframes, cudaMemcpyDeviceToHost, stream_));
+        LDPC_CUDA_CHECK(cudaMemcpyAsync(iterations, d_it.p, nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+        LDPC_CUDA_CHECK(cudaMemcpyAsync(posteriors, d_post.p, nframes * n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
         LDPC_CUDA_CHECK(cudaStreamSynchronize(stream_));
         return true;
     }
@@ -219,7 +308,7 @@ public:
         const size_t chunk_frames = plan_chunk_frames(nframes, 0);
         for (size_t f0 = 0; f0 < nframes; f0 += chunk_frames) {
             size_t nf = std::min(chunk_frames, nframes - f0);
-            if (!run_chunk((const uint8_t*)d_llrs + f0 * llrs_len * esz, is_f64, llrs_len, nf, max_iterations,
+            if (!run_chunk(ws_[0], (const uint8_t*)d_llrs + f0 * llrs_len * esz, is_f64, llrs_len, nf, max_iterations,
                            d_out + f0 * out_stride, out_len, out_stride, d_iterations + f0, stream))
                 return false;
         }
@@ -245,12 +334,18 @@ private:
     size_t elem_size() const { return impl_.dtype == Dtype::F64 ? 8 : (impl_.dtype == Dtype::F32 ? 4 : 1); }
     size_t bytes_per_128() const {
         const size_t E = (size_t)g_.E, n = (size_t)g_.n;
-        if (kind_ == Kind::FloodI8) return E * kLanes * 5 + n * kLanes * 4 + 2 * n * kLanes;
+        if (kind_ == Kind::FloodI8) return E * kLanes * 5 + n * kLanes * 4 + 2 * n * kLanes + (size_t)g_.m * kLanes;
         const size_t s = elem_size();
         if (kind_ == Kind::FloodFloat) return E * kTileFrames * s + E * kLanes + n * kTileFrames * s + 2 * n * kLanes;
         if (use_smem_layered_) return ell_size_ * kTileFrames * s;
         const size_t qs = impl_.dtype == Dtype::I8 ? 2 : s;
         return E * kTileFrames * s + n * kTileFrames * qs + 2 * n * kLanes;
+    }
+
+    size_t held_bytes() const {
+        size_t b = ws_[0].bytes() + ws_[1].bytes();
+        for (const auto& sl : slot_) b += sl.in.count + sl.out.count;
+        return b;
     }
 
     // frames per kernel launch: whole waves of resident CTAs, bounded by free HBM
@@ -259,8 +354,7 @@ private:
         size_t cap = max_tiles_opt_ > 0 ? (size_t)max_tiles_opt_ : (size_t)sm_count_ * (kind_ == Kind::FloodI8 ? 8 : 4);
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            size_t have = ws_bytes_ + d_stage_in_[0].count + d_stage_in_[1].count + d_stage_out_[0].count + d_stage_out_[1].count;
-            size_t budget = (size_t)((double)(free_b + have) * (staging_bytes_per_frame ? 0.85 : 0.45));
+            size_t budget = (size_t)((double)(free_b + held_bytes()) * (staging_bytes_per_frame ? 0.85 : 0.45));
             size_t fit = std::max<size_t>(budget / std::max<size_t>(bytes_per_128() + staging_bytes_per_frame * kTileFrames, 1), 1);
             cap = std::min(cap, fit);
         }
@@ -272,12 +366,85 @@ private:
         return frames;
     }
 
+    // Chunking of a host-buffer batch.  *lanes = 2: chunks of half a GPU-filling launch alternate between two
+    // compute streams / workspaces (int8 flooding on 512-frame tiles, batches of more than half a launch).
+    size_t plan_host_chunks(size_t nframes, size_t staging_bytes_per_frame, int* lanes) {
+        const size_t full = plan_chunk_frames(nframes, staging_bytes_per_frame);
+        *lanes = 1;
+        if (kind_ != Kind::FloodI8 || pick_nw(full) != 4 || getenv("LDPC_B200_ONE_LANE")) return full;
+        const size_t tf = (size_t)kTileFrames * 4;
+        const size_t half = full / 2 / tf * tf;
+        if (half < (size_t)sm_count_ * tf / 2 || nframes <= half || pick_nw(half) != 4) return full;
+        *lanes = 2;
+        return half;
+    }
+
+    bool ensure_pipeline() {
+        if (h2d_stream_) return true;
+        LDPC_CUDA_CHECK(cudaStreamCreateWithFlags(&h2d_stream_, cudaStreamNonBlocking));
+        LDPC_CUDA_CHECK(cudaStreamCreateWithFlags(&d2h_stream_, cudaStreamNonBlocking));
+        LDPC_CUDA_CHECK(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
+        for (auto& sl : slot_)
+            for (cudaEvent_t* e : {&sl.copied, &sl.ingested, &sl.emitted, &sl.drained}) LDPC_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        return true;
+    }
+
+    // H2D of one chunk into its staging slot, ingest + BP + emit on compute stream `cs`, D2H of the results
+    bool enqueue_chunk(StageSlot& sl, Workspace& ws, cudaStream_t cs, const void* h_llrs, bool is_f64, size_t llrs_len, size_t nf,
+                       uint32_t max_iterations, uint8_t* h_out, size_t out_len, size_t out_stride, int32_t* h_iters) {
+        const size_t esz = is_f64 ? 8 : 4;
+        if (sl.used) LDPC_CUDA_CHECK(cudaStreamWaitEvent(h2d_stream_, sl.ingested, 0));        // staging-in buffer consumed
+        LDPC_CUDA_CHECK(cudaMemcpyAsync(sl.in.p, h_llrs, nf * llrs_len * esz, cudaMemcpyHostToDevice, h2d_stream_));
+        LDPC_CUDA_CHECK(cudaEventRecord(sl.copied, h2d_stream_));
+        LDPC_CUDA_CHECK(cudaStreamWaitEvent(cs, sl.copied, 0));
+        if (sl.used) LDPC_CUDA_CHECK(cudaStreamWaitEvent(cs, sl.drained, 0));                   // staging-out buffer drained
+        if (!run_chunk(ws, sl.in.p, is_f64, llrs_len, nf, max_iterations, sl.out.p, out_len, out_len, sl.iters.p, cs, sl.ingested)) return false;
+        LDPC_CUDA_CHECK(cudaEventRecord(sl.emitted, cs));
+        LDPC_CUDA_CHECK(cudaStreamWaitEvent(d2h_stream_, sl.emitted, 0));
+        if (out_len)
+            LDPC_CUDA_CHECK(cudaMemcpy2DAsync(h_out, out_stride, sl.out.p, out_len, out_len, nf, cudaMemcpyDeviceToHost, d2h_stream_));
+        LDPC_CUDA_CHECK(cudaMemcpyAsync(h_iters, sl.iters.p, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, d2h_stream_));
+        LDPC_CUDA_CHECK(cudaEventRecord(sl.drained, d2h_stream_));
+        sl.used = true;
+        return true;
+    }
+
+    // Staircase variables (decoder_impl.hpp, RowMeta): degree 2, last slot of row r and second-to-last slot of
+    // row r+1, both rows inside one chunk of kFuseChunkRows rows and short enough for K1's register path.
+    bool build_row_meta() {
+        std::vector<RowMeta> meta((size_t)g_.m);
+        std::vector<int> fused_row((size_t)g_.n, -1);
+        auto deg_of = [&](int v) { return g_.col_ptr[(size_t)v + 1] - g_.col_ptr[(size_t)v]; };
+        auto row_deg = [&](int r) { return g_.row_ptr[(size_t)r + 1] - g_.row_ptr[(size_t)r]; };
+        const bool enable = !(getenv("LDPC_B200_FUSE") && atoi(getenv("LDPC_B200_FUSE")) == 0);
+        num_fused_ = 0;
+        for (int r = 0; r < g_.m; ++r) {
+            const int d = row_deg(r);
+            meta[(size_t)r] = RowMeta{g_.row_ptr[(size_t)r], d & 0xffff, -1, d > 0 ? g_.col_idx[(size_t)g_.row_ptr[(size_t)r + 1] - 1] : -1};
+        }
+        for (int r = 0; enable && r + 1 < g_.m; ++r) {
+            const int d0 = row_deg(r), d1 = row_deg(r + 1);
+            if ((r + 1) % kFuseChunkRows == 0 || d0 < 2 || d1 < 2 || d0 > kFuseMaxRowDeg || d1 > kFuseMaxRowDeg) continue;
+            const int v = g_.col_idx[(size_t)g_.row_ptr[(size_t)r + 1] - 1];
+            if (deg_of(v) != 2 || g_.col_idx[(size_t)g_.row_ptr[(size_t)r + 2] - 2] != v) continue;
+            if (d0 == 2 && (meta[(size_t)r].d_flags >> 16 & 1) && g_.col_idx[(size_t)g_.row_ptr[(size_t)r]] == v) continue;   // cannot be both slots of row r
+            meta[(size_t)r].d_flags |= 1 << 17;
+            meta[(size_t)r + 1].d_flags |= 1 << 16;
+            meta[(size_t)r + 1].fuse_var = v;
+            fused_row[(size_t)v] = r;
+            ++num_fused_;
+        }
+        h_fused_row_ = fused_row;
+        if (!d_row_meta_.upload(meta) || !d_fused_row_.upload(fused_row)) return false;
+        return true;
+    }
+
     // variables bucketed by degree so the variable pass runs fixed-degree, unrolled code
     bool build_var_classes() {
         std::vector<int> var_list, var_edges;
         vc_ = VarClasses{};
         int k = 0;
-        auto deg_of = [&](int v) { return g_.col_ptr[(size_t)v + 1] - g_.col_ptr[(size_t)v]; };
+        auto deg_of = [&](int v) { return h_fused_row_[(size_t)v] >= 0 ? 0 : g_.col_ptr[(size_t)v + 1] - g_.col_ptr[(size_t)v]; };   // fused: no class
         for (int d = 1; d <= 8; ++d) {
             int before = (int)var_list.size();
             int ebefore = (int)var_edges.size();
@@ -362,11 +529,10 @@ private:
         return true;
     }
 
-    bool run_chunk_smem_layered(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
+    bool run_chunk_smem_layered(Workspace& ws, const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
                                 size_t out_len, size_t out_stride, int32_t* d_iters, cudaStream_t s, cudaEvent_t after_ingest) {
         const size_t esz = layered_smem_rcv_elem(impl_.dtype == Dtype::F64, impl_.dtype == Dtype::I8);
-        if (!d_msg_.ensure(nf * ell_size_ * esz)) return false;
-        ws_bytes_ = d_msg_.count;
+        if (!ws.msg.ensure(nf * ell_size_ * esz)) return false;
         cudaEventRecord(ev_[0], s);
         cudaEventRecord(ev_[1], s);
         LayeredSmemLaunch L{};
@@ -375,8 +541,9 @@ private:
         L.is_f64 = impl_.dtype == Dtype::F64; L.is_i8 = impl_.dtype == Dtype::I8; L.hardlimit = impl_.hardlimit;
         L.threads = smem_threads_;
         L.llrs = d_llrs; L.in_f64 = is_f64; L.llrs_len = llrs_len; L.nframes = nf; L.src_map = punct_ ? d_src_map_.p : nullptr;
-        L.rcv = d_msg_.p; L.out = d_out; L.out_len = out_len; L.out_stride = out_stride; L.iters = d_iters;
+        L.rcv = ws.msg.p; L.out = d_out; L.out_len = out_len; L.out_stride = out_stride; L.iters = d_iters;
         L.max_iter = panics_ ? 0 : (int)std::min<uint32_t>(max_it, 0x7ffffff0u);
+        L.post = dump_post_;
         if (!launch_layered_smem(L, s)) return false;
         if (after_ingest) cudaEventRecord(after_ingest, s);     // the caller's LLR buffer is consumed by the decode kernel itself
         cudaEventRecord(ev_[2], s);
@@ -389,7 +556,7 @@ private:
         return true;
     }
 
-    bool ensure_workspace(size_t tiles, int nw) {
+    bool ensure_workspace(Workspace& ws, size_t tiles, int nw) {
         const size_t E = (size_t)g_.E, n = (size_t)g_.n;
         size_t msg_b, hbit_b, in_b, bits_b;
         if (kind_ == Kind::FloodI8) {
@@ -401,33 +568,33 @@ private:
             const size_t qs = impl_.dtype == Dtype::I8 ? 2 : elem_size();
             msg_b = tiles * E * kTileFrames * elem_size(); hbit_b = 1; in_b = tiles * n * kTileFrames * qs; bits_b = tiles * n * kLanes;
         }
-        if (!d_msg_.ensure(std::max<size_t>(msg_b, 1)) || !d_hbit_.ensure(std::max<size_t>(hbit_b, 1)) || !d_inq_.ensure(std::max<size_t>(in_b, 1)) ||
-            !d_hard_.ensure(std::max<size_t>(bits_b, 1)) || !d_final_.ensure(std::max<size_t>(bits_b, 1)))
+        if (!ws.msg.ensure(std::max<size_t>(msg_b, 1)) || !ws.hbit.ensure(std::max<size_t>(hbit_b, 1)) || !ws.inq.ensure(std::max<size_t>(in_b, 1)) ||
+            !ws.hard.ensure(std::max<size_t>(bits_b, 1)) || !ws.final_hard.ensure(std::max<size_t>(bits_b, 1)))
             return false;
-        ws_bytes_ = d_msg_.count + d_inq_.count + d_hbit_.count + d_hard_.count + d_final_.count;
+        if (kind_ == Kind::FloodI8 && !ws.cbit.ensure(std::max<size_t>(tiles * 2 * (size_t)g_.m * kLanes * (nw == 4 ? 2 : 1), 1))) return false;
         return true;
     }
 
     // One ingest -> BP kernel -> emit pass over nf frames.  ev_begin / ev_end select which of the four timing
     // events this pass records (a two-stage chunk spreads them over its passes).
-    bool run_pass(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
+    bool run_pass(Workspace& ws, const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
                   size_t out_len, size_t out_stride, int32_t* d_iters, cudaStream_t s, cudaEvent_t after_ingest = nullptr,
                   bool ev_begin = true, bool ev_end = true) {
-        if (use_smem_layered_) return run_chunk_smem_layered(d_llrs, is_f64, llrs_len, nf, max_it, d_out, out_len, out_stride, d_iters, s, after_ingest);
+        if (use_smem_layered_) return run_chunk_smem_layered(ws, d_llrs, is_f64, llrs_len, nf, max_it, d_out, out_len, out_stride, d_iters, s, after_ingest);
         const int nw = pick_nw(nf);
         const size_t tf = (size_t)kTileFrames * nw;
         const int tiles = (int)((nf + tf - 1) / tf);
-        if (!ensure_workspace((size_t)tiles, nw)) return false;
-        if (!d_iters_tile_.ensure((size_t)tiles * tf)) return false;
+        if (!ensure_workspace(ws, (size_t)tiles, nw)) return false;
+        if (!ws.iters_tile.ensure((size_t)tiles * tf)) return false;
         if (ev_begin) cudaEventRecord(ev_[0], s);
         IngestLaunch in{};
         in.llrs = d_llrs; in.is_f64 = is_f64; in.llrs_len = llrs_len; in.nframes = nf; in.n = g_.n;
         in.src_map = punct_ ? d_src_map_.p : nullptr; in.num_tiles = tiles; in.words_per_lane = nw;
-        in.hard = d_hard_.p;
-        if (kind_ == Kind::FloodI8) in.inq_i8 = reinterpret_cast<uint32_t*>(d_inq_.p);
-        else if (impl_.dtype == Dtype::F32) in.in_f32 = reinterpret_cast<float*>(d_inq_.p);
-        else if (impl_.dtype == Dtype::F64) in.in_f64 = reinterpret_cast<double*>(d_inq_.p);
-        else in.in_i16 = reinterpret_cast<int16_t*>(d_inq_.p);
+        in.hard = ws.hard.p;
+        if (kind_ == Kind::FloodI8) in.inq_i8 = reinterpret_cast<uint32_t*>(ws.inq.p);
+        else if (impl_.dtype == Dtype::F32) in.in_f32 = reinterpret_cast<float*>(ws.inq.p);
+        else if (impl_.dtype == Dtype::F64) in.in_f64 = reinterpret_cast<double*>(ws.inq.p);
+        else in.in_i16 = reinterpret_cast<int16_t*>(ws.inq.p);
         if (!launch_ingest(in, s)) return false;
         if (ev_begin) cudaEventRecord(ev_[1], s);
         if (after_ingest) cudaEventRecord(after_ingest, s);
@@ -436,8 +603,9 @@ private:
         if (kind_ == Kind::FloodI8) {
             FloodI8Launch fl{};
             fl.graph = dg_; fl.classes = vc_; fl.num_tiles = tiles; fl.words_per_lane = nw;
-            fl.msg = reinterpret_cast<uint32_t*>(d_msg_.p); fl.hbit = d_hbit_.p; fl.inq = reinterpret_cast<const uint32_t*>(d_inq_.p);
-            fl.raw0 = d_hard_.p; fl.final_hard = d_final_.p; fl.iters = d_iters_tile_.p; fl.max_iter = max_iter;
+            fl.msg = reinterpret_cast<uint32_t*>(ws.msg.p); fl.hbit = ws.hbit.p; fl.inq = reinterpret_cast<const uint32_t*>(ws.inq.p);
+            fl.raw0 = ws.hard.p; fl.final_hard = ws.final_hard.p; fl.iters = ws.iters_tile.p; fl.max_iter = max_iter;
+            fl.row_meta = d_row_meta_.p; fl.fused_row = d_fused_row_.p; fl.cbit = ws.cbit.p;
             fl.aminstar = impl_.rule == Rule::Aminstar; fl.jones = impl_.jones; fl.hardlimit = impl_.hardlimit; fl.deg1clip = impl_.deg1clip;
             fl.cluster = 1;
             while (fl.cluster < 16 && tiles * fl.cluster * 2 <= 2 * sm_count_) fl.cluster *= 2;     // up to ~2 CTAs per SM
@@ -448,9 +616,10 @@ private:
             gl.graph = dg_; gl.num_tiles = tiles; gl.is_f64 = impl_.dtype == Dtype::F64; gl.is_i8 = impl_.dtype == Dtype::I8;
             gl.hardlimit = impl_.hardlimit;
             gl.rule = impl_.rule == Rule::Phi ? kPhi : impl_.rule == Rule::Tanh ? kTanh : impl_.rule == Rule::Minstarapprox ? kMinstarapprox : kAminstar;
-            gl.msg = d_msg_.p; gl.hbit = d_hbit_.p; gl.in = d_inq_.p; gl.in_out_q = d_inq_.p;
-            gl.raw0 = d_hard_.p; gl.final_hard = d_final_.p; gl.iters = d_iters_tile_.p; gl.max_iter = max_iter;
+            gl.msg = ws.msg.p; gl.hbit = ws.hbit.p; gl.in = ws.inq.p; gl.in_out_q = ws.inq.p;
+            gl.raw0 = ws.hard.p; gl.final_hard = ws.final_hard.p; gl.iters = ws.iters_tile.p; gl.max_iter = max_iter;
             gl.level_ptr = d_level_ptr_.p; gl.level_rows = d_level_rows_.p; gl.num_levels = num_levels_;
+            gl.post = dump_post_tiles_;
             gl.cluster = 1;
             while (gl.cluster < 8 && tiles * gl.cluster * 2 <= 2 * sm_count_) gl.cluster *= 2;      // up to ~2 CTAs per SM
             if (const char* e = getenv("LDPC_B200_CLUSTER")) gl.cluster = atoi(e);
@@ -458,10 +627,10 @@ private:
         }
         if (ev_end) cudaEventRecord(ev_[2], s);
         EmitLaunch em{};
-        em.final_hard = d_final_.p; em.n = g_.n; em.num_tiles = tiles; em.words_per_lane = nw; em.nframes = nf; em.out = d_out; em.out_len = out_len;
+        em.final_hard = ws.final_hard.p; em.n = g_.n; em.num_tiles = tiles; em.words_per_lane = nw; em.nframes = nf; em.out = d_out; em.out_len = out_len;
         em.out_stride = out_stride;
         if (!launch_emit(em, s)) return false;
-        LDPC_CUDA_CHECK(cudaMemcpyAsync(d_iters, d_iters_tile_.p, nf * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        LDPC_CUDA_CHECK(cudaMemcpyAsync(d_iters, ws.iters_tile.p, nf * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
         if (panics_ && max_it > 0) {
             if (!launch_mark_panics(d_iters, nf, s)) return false;
         }
@@ -499,15 +668,15 @@ private:
         return best_cost < 0.9 * single ? best_m : 0;
     }
 
-    bool run_chunk(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
+    bool run_chunk(Workspace& ws, const void* d_llrs, bool is_f64, size_t llrs_len, size_t nf, uint32_t max_it, uint8_t* d_out,
                    size_t out_len, size_t out_stride, int32_t* d_iters, cudaStream_t s, cudaEvent_t after_ingest = nullptr) {
         const uint32_t m1 = two_stage_m1(max_it, nf);
         if (m1 == 0) {
-            if (!run_pass(d_llrs, is_f64, llrs_len, nf, max_it, d_out, out_len, out_stride, d_iters, s, after_ingest)) return false;
+            if (!run_pass(ws, d_llrs, is_f64, llrs_len, nf, max_it, d_out, out_len, out_stride, d_iters, s, after_ingest)) return false;
             return record_histogram(d_iters, nf, max_it, s);
         }
         const size_t esz = is_f64 ? 8 : 4;
-        if (!run_pass(d_llrs, is_f64, llrs_len, nf, m1, d_out, out_len, out_stride, d_iters, s, nullptr, true, false)) return false;
+        if (!run_pass(ws, d_llrs, is_f64, llrs_len, nf, m1, d_out, out_len, out_stride, d_iters, s, nullptr, true, false)) return false;
         if (!d_fail_idx_.ensure(nf + 1)) return false;
         LDPC_CUDA_CHECK(cudaMemsetAsync(d_fail_idx_.p + nf, 0, sizeof(int32_t), s));
         if (!launch_collect_failed(d_iters, nf, d_fail_idx_.p, d_fail_idx_.p + nf, s)) return false;
@@ -524,7 +693,7 @@ private:
             const size_t c = std::min(cap, (size_t)count - off);
             const bool last = off + c >= (size_t)count;
             if (!launch_gather_rows(d_llrs, llrs_len * esz, d_fail_idx_.p + off, c, d_llrs2_.p, s)) return false;
-            if (!run_pass(d_llrs2_.p, is_f64, llrs_len, c, max_it, d_out2_.p, out_len, out_len, d_iters2_.p, s, nullptr, false, last)) return false;
+            if (!run_pass(ws, d_llrs2_.p, is_f64, llrs_len, c, max_it, d_out2_.p, out_len, out_len, d_iters2_.p, s, nullptr, false, last)) return false;
             if (!launch_scatter_results(d_out2_.p, out_len, d_iters2_.p, d_fail_idx_.p + off, c, d_out, out_stride, d_iters, s)) return false;
         }
         if (count == 0) { cudaEventRecord(ev_[2], s); cudaEventRecord(ev_[3], s); }
@@ -575,7 +744,6 @@ private:
     size_t expected_len_ = 0;
     bool panics_ = false;
     int device_ = 0, sm_count_ = 148, max_tiles_opt_ = 0, nw_opt_ = 0;
-    size_t ws_bytes_ = 0;
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timed_ = false;
@@ -583,6 +751,10 @@ private:
     enum class Kind { FloodI8, FloodFloat, Layered };
     Kind kind_ = Kind::FloodI8;
     DevBuf<int> d_row_ptr_, d_col_idx_, d_col_ptr_, d_col_edge_, d_src_map_, d_var_list_, d_var_edges_, d_level_ptr_, d_level_rows_;
+    DevBuf<RowMeta> d_row_meta_;
+    DevBuf<int> d_fused_row_;
+    std::vector<int> h_fused_row_;
+    int num_fused_ = 0;
     VarClasses vc_{};
     int num_levels_ = 0;
     bool use_smem_layered_ = false;
@@ -591,9 +763,16 @@ private:
     LayeredSmemGraph sg_{};
     size_t ell_size_ = 1;
     int smem_threads_ = 256;
-    DevBuf<uint8_t> d_msg_, d_inq_;
-    DevBuf<uint8_t> d_hbit_, d_hard_, d_final_, d_stage_in_[2], d_stage_out_[2];
-    DevBuf<int32_t> d_iters_tile_, d_stage_iters_[2], d_fail_idx_, d_iters2_;
+    void* dump_post_tiles_ = nullptr;  // test hook (decode_batch_posteriors): K2 posterior tiles
+    double* dump_post_ = nullptr;      // test hook: K3q posteriors [nframes][n]
+    Workspace ws_[2];                  // [0]: device-buffer path and lane 0 of the host path; [1]: lane 1
+    StageSlot slot_[2];
+    size_t slot_counter_ = 0;
+    struct Ticket { int64_t id = 0; cudaEvent_t done = nullptr; };
+    std::deque<Ticket> tickets_;
+    int64_t next_ticket_ = 0;
+    cudaStream_t stream2_ = nullptr;
+    DevBuf<int32_t> d_fail_idx_, d_iters2_;
     DevBuf<uint8_t> d_llrs2_, d_out2_;
     DevBuf<unsigned int> d_hist_;
     unsigned int* h_hist_ = nullptr;
@@ -602,7 +781,6 @@ private:
     uint32_t hist_max_it_ = 0;
     long long two_stage_chunks_ = 0;
     cudaStream_t h2d_stream_ = nullptr, d2h_stream_ = nullptr;
-    cudaEvent_t ev_copied_[2] = {}, ev_ingested_[2] = {}, ev_emitted_[2] = {}, ev_drained_[2] = {};
 };
 
 __global__ void mark_panics_kernel(int32_t* iters, size_t nf) {

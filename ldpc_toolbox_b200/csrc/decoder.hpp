@@ -41,6 +41,15 @@ public:
     // which the first out_len are written; iterations[f] >= 0 on success, -1 on failure.
     virtual bool decode_batch(const void* llrs, bool is_f64, size_t llrs_len, size_t nframes, uint32_t max_iterations,
                               uint8_t* out, size_t out_len, size_t out_stride, int32_t* iterations) = 0;
+    // Asynchronous form of decode_batch: returns a ticket (>= 0) as soon as the work is enqueued, -1 on an
+    // argument / CUDA error.  The caller's buffers must stay valid (and, to overlap, pinned) until wait(ticket)
+    // returns; tickets complete in submission order.  decode_batch = submit_batch + wait.
+    virtual int64_t submit_batch(const void* llrs, bool is_f64, size_t llrs_len, size_t nframes, uint32_t max_iterations,
+                                 uint8_t* out, size_t out_len, size_t out_stride, int32_t* iterations) = 0;
+    virtual bool wait(int64_t ticket) = 0;
+    // Test hook: decode_batch that also returns the posterior LLRs [nframes][n] as f64 (float decoders only).
+    virtual bool decode_batch_posteriors(const void* llrs, bool is_f64, size_t llrs_len, size_t nframes, uint32_t max_iterations,
+                                         uint8_t* out, size_t out_len, size_t out_stride, int32_t* iterations, double* posteriors) = 0;
     // Same on device buffers (inputs already resident in HBM), asynchronous on `stream`.
     virtual bool decode_batch_device(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nframes,
                                      uint32_t max_iterations, uint8_t* d_out, size_t out_len, size_t out_stride,

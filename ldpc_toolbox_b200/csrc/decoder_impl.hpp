@@ -42,6 +42,8 @@ struct EmitLaunch {
     size_t out_len, out_stride;
 };
 bool launch_emit(const EmitLaunch& L, cudaStream_t stream);
+// test hook: posteriors of the float flooding kernel, tiles [tiles][n][128] (f32 / f64) -> [nframes][n] f64
+bool launch_emit_posteriors(const void* post_tiles, bool is_f64, int n, size_t nframes, double* out, cudaStream_t stream);
 
 // Variables grouped by degree (host-built, device-resident): class k holds the variables
 // var_list[off[k] .. off[k+1]) which all have degree deg[k] (1..8), with their row-major edge ids
@@ -58,9 +60,27 @@ struct VarClasses {
 };
 
 // ---- flood_i8.cu -------------------------------------------------------------------------------
+// Staircase fusion (DVB-S2 and other IRA codes, reference src/codes/dvbs2.rs:92-96): a degree-2 variable whose
+// two checks are consecutive rows r, r+1 — last slot of row r, second-to-last slot of row r+1 — is updated
+// inside the check pass, right after both of its incoming messages of the iteration exist, by the warp that
+// owns both rows; its messages then cross HBM twice per iteration instead of four times.  Exact under
+// flooding: the variable update of iteration i depends only on the two check outputs of iteration i.
+// Rows are dealt to warps in chunks of kFuseChunkRows consecutive rows; a staircase variable that straddles
+// two chunks stays in the ordinary variable pass.
+constexpr int kFuseChunkRows = 32;
+constexpr int kFuseMaxRowDeg = 8;
+struct RowMeta {             // one 16-byte record per check row
+    int e0;                  // first row-major edge
+    int d_flags;             // bits 0-15 degree, bit 16: slot d-2 is fused with row r-1, bit 17: slot d-1 is fused with row r+1
+    int fuse_var;            // variable of the slot fused with row r-1 (its channel LLR line), or -1
+    int last_var;            // variable of the last slot (raw-sign line of the fused variable at start-up)
+};
 struct FloodI8Launch {
     DeviceGraph graph;
     VarClasses classes;
+    const RowMeta* row_meta; // m records
+    const int* fused_row;    // n entries: row r whose last slot holds the variable when it is fused, else -1
+    void* cbit;              // [tiles][2][m][32] hard decisions of the fused variables, by iteration parity (u8 / u16 per lane)
     int num_tiles;
     int words_per_lane;      // 1 or 4
     uint32_t* msg;
@@ -94,6 +114,7 @@ struct GenericLaunch {
     const int* level_rows;
     int num_levels;
     int cluster;            // flooding: CTAs per tile (thread-block cluster of 1, 2, 4 or 8), small batches fill the GPU this way
+    void* post;             // flooding, test hook (may be null): posteriors F [tiles][n][128] of each frame's last processed iteration
 };
 bool launch_flood_float(const GenericLaunch& L, cudaStream_t stream);
 bool launch_layered(const GenericLaunch& L, cudaStream_t stream);
@@ -134,6 +155,7 @@ struct LayeredSmemLaunch {
     size_t out_len, out_stride;
     int32_t* iters;          // device, [nframes]
     int max_iter;
+    double* post;            // test hook (may be null): device, [nframes][n] posteriors (Qv) at the end of each frame's decode
 };
 bool launch_layered_smem(const LayeredSmemLaunch& L, cudaStream_t stream);
 size_t layered_smem_bytes(int n, bool is_f64, bool is_i8);

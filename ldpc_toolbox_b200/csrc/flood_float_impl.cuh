@@ -31,6 +31,7 @@ struct FloodFloatParams {
     uint8_t* final_hard;    // [tiles][n][32]
     int32_t* iters;         // [tiles*128]
     int max_iter;
+    F* post;                // test hook (may be null): [tiles][n][128] output_llrs of each frame's last processed iteration (flooding.rs:111-125)
 };
 
 // L2-only access to the message state: with a thread-block cluster per tile the check pass and the
@@ -83,7 +84,8 @@ __device__ __forceinline__ void flood_check_row(F* __restrict__ msg, size_t e0, 
 // message on edge e = llr - c_e.  DT > 0: all lines are requested before the first is used.
 template <class F, int DT>
 __device__ __forceinline__ void flood_var_node(F* __restrict__ msg, uint8_t* __restrict__ hbit, const V4<F>& inp,
-                                               const int* __restrict__ col_edge, int d_rt, int lane) {
+                                               const int* __restrict__ col_edge, int d_rt, int lane, F* __restrict__ post, size_t v,
+                                               uint32_t live) {
     constexpr int CAP = DT > 0 ? DT : 1;
     const int d = DT > 0 ? DT : d_rt;
     F sum[4] = {F(0), F(0), F(0), F(0)};
@@ -109,6 +111,13 @@ __device__ __forceinline__ void flood_var_node(F* __restrict__ msg, uint8_t* __r
     uint32_t hb = 0;
 #pragma unroll
     for (int f = 0; f < 4; ++f) { llr[f] = inp.v[f] + sum[f]; hb |= (uint32_t)(llr[f] <= F(0)) << f; }
+    if (post) {                       // frames that already stopped keep the posterior of their last iteration
+        V4<F> pw = ld4cg<F>(post, v, lane);
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+            if (live >> f & 1) pw.v[f] = llr[f];
+        st4cg<F>(post, v, lane, pw);
+    }
     if (DT > 0) {
 #pragma unroll
         for (int j = 0; j < d; ++j) {
@@ -151,6 +160,7 @@ __global__ void __launch_bounds__(kGWarps * 32, sizeof(F) == 8 ? 1 : 2) flood_fl
     const uint8_t* raw0 = p.raw0 + tile * (size_t)g.n * kLanes;
     uint8_t* fin = p.final_hard + tile * (size_t)g.n * kLanes;
     int32_t* iters = p.iters + tile * kTileFrames;
+    F* post = p.post ? p.post + tile * (size_t)g.n * kTileFrames : nullptr;
     if (threadIdx.x < kLanes) { s_unsat[0][threadIdx.x] = 0; s_unsat[1][threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
 
     // flooding.rs:88-100
@@ -226,17 +236,18 @@ __global__ void __launch_bounds__(kGWarps * 32, sizeof(F) == 8 ? 1 : 2) flood_fl
         const int all = __syncthreads_and(((done | stop) & 0xfu) == 0xfu);
         if (all || last) break;
 
+        const uint32_t live = ~s_done[lane] & 0xfu;
         for (int v = gw; v < g.n; v += nw) {                             // flooding.rs:111-125
             const int p0 = __ldg(g.col_ptr + v), d = __ldg(g.col_ptr + v + 1) - p0;
             const V4<F> inp = ld4<F>(in, (size_t)v, lane);
             const int* ce = g.col_edge + p0;
-#define LDPC_VAR_CASE(D_) case D_: flood_var_node<F, D_>(msg, hbit, inp, ce, d, lane); break;
+#define LDPC_VAR_CASE(D_) case D_: flood_var_node<F, D_>(msg, hbit, inp, ce, d, lane, post, (size_t)v, live); break;
             switch (d) {
                 case 0: break;
                 LDPC_VAR_CASE(1) LDPC_VAR_CASE(2) LDPC_VAR_CASE(3) LDPC_VAR_CASE(4) LDPC_VAR_CASE(5) LDPC_VAR_CASE(6)
                 LDPC_VAR_CASE(7) LDPC_VAR_CASE(8) LDPC_VAR_CASE(9) LDPC_VAR_CASE(10) LDPC_VAR_CASE(11) LDPC_VAR_CASE(12)
                 LDPC_VAR_CASE(13)
-                default: flood_var_node<F, 0>(msg, hbit, inp, ce, d, lane); break;
+                default: flood_var_node<F, 0>(msg, hbit, inp, ce, d, lane, post, (size_t)v, live); break;
             }
 #undef LDPC_VAR_CASE
         }
@@ -251,6 +262,7 @@ static bool launch_flood_float_t(const GenericLaunch& L, cudaStream_t stream) {
     FloodFloatParams<F> p;
     p.g = L.graph; p.msg = static_cast<F*>(L.msg); p.hbit = L.hbit; p.in = static_cast<const F*>(L.in);
     p.raw0 = L.raw0; p.final_hard = L.final_hard; p.iters = L.iters; p.max_iter = L.max_iter;
+    p.post = static_cast<F*>(L.post);
     const int C = L.cluster >= 1 && L.cluster <= 8 ? L.cluster : 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)L.num_tiles * (unsigned)C);

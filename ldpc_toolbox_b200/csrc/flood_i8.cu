@@ -58,6 +58,9 @@ struct FloodI8Params {
     const uint32_t* inq;    // [tiles][n][32][NW] quantised channel LLRs (int8 x4 per word)
     const void* raw0;       // [tiles][n][32]     raw-sign hard decisions (x <= 0.0), 4*NW bits per lane
     void* final_hard;       // [tiles][n][32]     snapshot taken when a frame stops
+    const RowMeta* row_meta;  // [m]              per-row record: first edge, degree, staircase-fusion flags (decoder_impl.hpp)
+    const int* fused_row;     // [n]              row whose last slot holds the variable when it is fused, else -1
+    void* cbit;             // [tiles][2][m][32]  hard decisions of the fused variables by iteration parity, 4*NW bits per lane
     int32_t* iters;         // [tiles*128*NW]     iterations, or -1 on failure
     int max_iter;
     int num_tiles;
@@ -293,35 +296,6 @@ __device__ __forceinline__ void check_word(uint32_t (&x)[D], uint32_t skip, cons
     for (int j = 0; j < D; ++j) x[j] = apply_signs(om[j], sign_excluding<D - 1>(S, x[j]), k);
 }
 
-template <int NW, int MAXD, int D, bool AMIN, bool HLIM>
-__device__ __forceinline__ void check_fixed(Lane<NW> (&x)[MAXD], uint32_t* __restrict__ msg, size_t e0, int lane,
-                                            uint32_t skip, const Tables& tb, const Consts& k) {
-    if (skip == 0) {
-#pragma unroll
-        for (int q = 0; q < NW; ++q) {
-            uint32_t xw[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) xw[j] = x[j].w[q];
-            check_word<D, AMIN, HLIM, false>(xw, 0, tb, k);
-#pragma unroll
-            for (int j = 0; j < D; ++j) x[j].w[q] = xw[j];
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < NW; ++q) {
-            if (((skip >> (4 * q)) & 0xfu) == 0xfu) continue;
-            uint32_t xw[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) xw[j] = x[j].w[q];
-            check_word<D, AMIN, HLIM, true>(xw, skip >> (4 * q), tb, k);
-#pragma unroll
-            for (int j = 0; j < D; ++j) x[j].w[q] = xw[j];
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < D; ++j) st_lane<NW>(msg, e0 + j, lane, x[j]);
-}
-
 // any degree up to kMaxGenericD; one word at a time, inputs staged in local memory
 template <int NW, bool AMIN, bool HLIM>
 __device__ __noinline__ void check_generic(uint32_t* __restrict__ msg, size_t e0, int d, int lane, uint32_t skip, const Tables& tb,
@@ -412,6 +386,60 @@ __device__ __forceinline__ uint32_t var_message(uint32_t c_ob, uint32_t base_lo,
     uint32_t vlo = __vmaxs2(__viaddmin_s16x2(ulo, negK, 0x00ff00ffu), 0x00010001u);
     uint32_t vhi = __vmaxs2(__viaddmin_s16x2(uhi, negK, 0x00ff00ffu), 0x00010001u);
     return prmt(vlo, vhi, 0x6420);
+}
+
+// One check of degree D on the register path: the check-node rule word by word, then — staircase fusion,
+// decoder_impl.hpp — the degree-2 variable this row shares with the previous row (slot D-2) is updated on the
+// spot from `carry` (the previous row's message to it, kept in registers), x[D-2] and its channel LLRs `inl`:
+// both of its outgoing messages and its hard decision are final for this iteration.  The previous row's last
+// line is stored now (deferred by one row); this row's last line is kept in `carry` when the next row fuses.
+template <int NW, int MAXD, int D, bool AMIN, bool HLIM>
+__device__ __forceinline__ void check_fixed(Lane<NW> (&x)[MAXD], uint32_t* __restrict__ msg, size_t e0, int lane, uint32_t skip,
+                                            const Tables& tb, const Consts& k, bool fuse_prev, bool fuse_next, Lane<NW>& carry,
+                                            const Lane<NW>& inl, bool jones, typename HBitsT<NW>::type* __restrict__ cnew_prev) {
+    if (skip == 0) {
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            uint32_t xw[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) xw[j] = x[j].w[q];
+            check_word<D, AMIN, HLIM, false>(xw, 0, tb, k);
+#pragma unroll
+            for (int j = 0; j < D; ++j) x[j].w[q] = xw[j];
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            if (((skip >> (4 * q)) & 0xfu) == 0xfu) continue;
+            uint32_t xw[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) xw[j] = x[j].w[q];
+            check_word<D, AMIN, HLIM, true>(xw, skip >> (4 * q), tb, k);
+#pragma unroll
+            for (int j = 0; j < D; ++j) x[j].w[q] = xw[j];
+        }
+    }
+    if (fuse_prev) {
+        const VarConsts vk = var_consts(2, jones);
+        uint32_t hb = 0;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            VarAcc sum = widen(inl.w[q]);
+            const VarAcc ca = widen(carry.w[q]), cb = widen(x[D - 2].w[q]);
+            sum.lo = (uint32_t)imad((int)ca.lo, k.one, (int)sum.lo) + cb.lo;
+            sum.hi = (uint32_t)imad((int)ca.hi, k.one, (int)sum.hi) + cb.hi;
+            uint32_t blo, bhi;
+            hb |= var_posterior(sum, vk, blo, bhi) << (4 * q);
+            carry.w[q] = var_message(carry.w[q], blo, bhi, vk.negK, k);
+            x[D - 2].w[q] = var_message(x[D - 2].w[q], blo, bhi, vk.negK, k);
+        }
+        st_lane<NW>(msg, e0 - 1, lane, carry);            // the previous row's last edge is this row's first edge - 1
+        cnew_prev[lane] = (typename HBitsT<NW>::type)hb;
+    }
+#pragma unroll
+    for (int j = 0; j + 1 < D; ++j) st_lane<NW>(msg, e0 + j, lane, x[j]);
+    if (fuse_next) carry = x[D - 1];
+    else st_lane<NW>(msg, e0 + D - 1, lane, x[D - 1]);
 }
 
 // U variables of degree D per warp iteration: all index loads, then all message loads, then math.
@@ -519,7 +547,9 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
     constexpr uint32_t kAll = NW == 1 ? 0xfu : 0xffffu;
     constexpr int kFrames = kTileFrames * NW;
     constexpr int kMsgBytes = MAXD * kLanes * NW * 4;                 // one check's message lines
-    constexpr int kStageBytes = kMsgBytes + MAXD * kLanes * (int)sizeof(HB);
+    constexpr int kInqOff = kMsgBytes + MAXD * kLanes * (int)sizeof(HB);   // channel LLRs of the variable fused with the previous row
+    constexpr int kCbitOff = kInqOff + kLanes * NW * 4;                    // previous hard decisions of the variable fused with the next row
+    constexpr int kStageBytes = kCbitOff + kLanes * (int)sizeof(HB);
     extern __shared__ __align__(16) uint8_t dsm[];                    // [kGroups * kWarps][2][kStageBytes]
     __shared__ __align__(128) Tables tb;
     __shared__ uint32_t s_unsat_g[kGroups][2][kLanes];      // [iteration parity]: no reset race between the CTAs of a cluster
@@ -555,7 +585,9 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
     const uint32_t* inq = p.inq + tile * (size_t)g.n * kLanes * NW;
     const HB* raw0 = static_cast<const HB*>(p.raw0) + tile * (size_t)g.n * kLanes;
     HB* fin = static_cast<HB*>(p.final_hard) + tile * (size_t)g.n * kLanes;
+    HB* cbit = static_cast<HB*>(p.cbit) + tile * (size_t)2 * g.m * kLanes;
     int32_t* iters = p.iters + tile * kFrames;
+    const bool jones = p.jones != 0, d1c = p.deg1clip != 0;
 
     for (int i = threadIdx.x; i < 255; i += blockDim.x) {
         int d = i - 127;
@@ -583,6 +615,10 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
         for (int u = 0; u < 4; ++u)
             if (e0 + u < g.E) { st_lane<NW>(msg, (size_t)(e0 + u), lane, w[u]); hbit[(size_t)(e0 + u) * kLanes + lane] = hb[u]; }
     }
+    for (int r = gw; active && r < g.m; r += nw) {
+        const int4 mt = __ldg(reinterpret_cast<const int4*>(p.row_meta) + r);
+        if ((mt.y >> 17) & 1) cbit[(size_t)r * kLanes + lane] = raw0[(size_t)mt.w * kLanes + lane];
+    }
     if (C > 1) cluster.sync();
     else __syncthreads();
     PROF_T(pt_init1);
@@ -604,38 +640,55 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
         // the lines about to be fetched through the async proxy (TMA) were written through the generic proxy
         asm volatile("fence.proxy.async.global;" ::: "memory");
         {
-            // Per-warp double buffer in shared memory: the messages and hard bits of check c+kWarps stream
-            // in while check c is being computed, at no register cost.  A check's D message lines (and its
-            // D hard-bit lines) are contiguous in HBM, so one elected lane moves each with a single TMA bulk
-            // copy (cp.async.bulk) that completes on the stage's mbarrier.
+            // Per-warp double buffer in shared memory: the messages and hard bits of the warp's next check stream
+            // in while the current one is being computed, at no register cost.  A check's D message lines (and
+            // its hard-bit lines) are contiguous in HBM, so one elected lane moves each with a single TMA bulk
+            // copy (cp.async.bulk) that completes on the stage's mbarrier.  Rows are dealt to warps in chunks of
+            // kFuseChunkRows consecutive rows (staircase fusion, decoder_impl.hpp): a stage also receives the
+            // channel-LLR line of the variable fused with the previous row and the previous-iteration hard
+            // decisions of the variable fused with the next row.
             uint8_t* wbuf = dsm + (size_t)cta_warp * 2 * kStageBytes;
-            // row_ptr of the check after next is fetched one step early, so issuing a stage never waits on it
-            auto row_of = [&](int c, int& e0o, int& dout) {
-                const int cc = min(c, g.m - 1);
-                e0o = __ldg(g.row_ptr + cc);
-                dout = __ldg(g.row_ptr + cc + 1) - e0o;
-            };
-            auto issue = [&](int stage, int e0, int d) {
+            const HB* cold = cbit + (size_t)((it - 1) & 1) * g.m * kLanes;      // hard decisions of iteration it-1
+            HB* cnew = cbit + (size_t)(it & 1) * g.m * kLanes;                  // ... of iteration it
+            auto next_row = [&](int r) { const int n1 = r + 1; return (n1 % kFuseChunkRows) ? n1 : n1 + (nw - 1) * kFuseChunkRows; };
+            // the record of the row after next is fetched one step early, so issuing a stage never waits on it
+            auto meta_of = [&](int r) { return __ldg(reinterpret_cast<const int4*>(p.row_meta) + min(r, g.m - 1)); };
+            auto issue = [&](int stage, int r, const int4& mt) {
+                const int d = mt.y & 0xffff;
                 if (d <= MAXD && d > 0 && lane == 0) {
+                    const bool fp = (mt.y >> 16) & 1, fn = (mt.y >> 17) & 1;
                     uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
-                    const uint32_t mb = last ? 0u : (uint32_t)d * kLanes * NW * 4, hbytes = (uint32_t)d * kLanes * (uint32_t)sizeof(HB);
-                    mbar_expect_tx(&s_bar[cta_warp][stage], mb + hbytes);
-                    if (!last) bulk_g2s(sb, msg + (size_t)e0 * kLanes * NW, mb, &s_bar[cta_warp][stage]);
-                    bulk_g2s(sb + kMsgBytes, hbit + (size_t)e0 * kLanes, hbytes, &s_bar[cta_warp][stage]);
+                    const uint32_t mb = last ? 0u : (uint32_t)d * kLanes * NW * 4;
+                    const uint32_t nh = (uint32_t)(d - (fn ? (fp ? 2 : 1) : 0));           // trailing fused slots have no hbit line
+                    const uint32_t hbytes = nh * kLanes * (uint32_t)sizeof(HB);
+                    const uint32_t ib = (fp && !last) ? (uint32_t)kLanes * NW * 4 : 0u, cb = fn ? (uint32_t)kLanes * (uint32_t)sizeof(HB) : 0u;
+                    mbar_expect_tx(&s_bar[cta_warp][stage], mb + hbytes + ib + cb);
+                    if (mb) bulk_g2s(sb, msg + (size_t)mt.x * kLanes * NW, mb, &s_bar[cta_warp][stage]);
+                    if (hbytes) bulk_g2s(sb + kMsgBytes, hbit + (size_t)mt.x * kLanes, hbytes, &s_bar[cta_warp][stage]);
+                    if (ib) bulk_g2s(sb + kInqOff, inq + (size_t)mt.z * kLanes * NW, ib, &s_bar[cta_warp][stage]);
+                    if (cb) bulk_g2s(sb + kCbitOff, cold + (size_t)r * kLanes, cb, &s_bar[cta_warp][stage]);
                 }
             };
-            int c = gw, stage = 0, e0c = 0, dc = 0, e0n = 0, dn = 0;
-            if (c < g.m) {
-                row_of(c, e0c, dc);
-                row_of(c + nw, e0n, dn);
-                issue(0, e0c, dc);
+            int r = gw * kFuseChunkRows, stage = 0;
+            int4 mc = make_int4(0, 0, -1, -1), mn = mc;
+            if (r < g.m) {
+                mc = meta_of(r);
+                mn = meta_of(next_row(r));
+                issue(0, r, mc);
             }
-            for (; c < g.m; c += nw, stage ^= 1) {
-                const int e0 = e0c, d = dc;
-                e0c = e0n; dc = dn;
-                if (c + nw < g.m) {
-                    issue(stage ^ 1, e0c, dc);
-                    row_of(c + 2 * nw, e0n, dn);
+            Lane<NW> carry;                  // this warp's message to the variable fused with the next row
+#pragma unroll
+            for (int q = 0; q < NW; ++q) carry.w[q] = 0;
+            uint32_t cold_prev = 0;          // previous-iteration hard decisions of the variable fused with the previous row
+            for (; r < g.m; stage ^= 1) {
+                const int4 mt = mc;
+                const int e0 = mt.x, d = mt.y & 0xffff;
+                const bool fuse_prev = (mt.y >> 16) & 1, fuse_next = (mt.y >> 17) & 1;
+                const int rn = next_row(r);
+                mc = mn;
+                if (rn < g.m) {
+                    issue(stage ^ 1, rn, mc);
+                    mn = meta_of(next_row(rn));
                 }
                 if (d <= MAXD && d > 0) {
                     mbar_wait(&s_bar[cta_warp][stage], (bar_phase >> stage) & 1u);
@@ -646,33 +699,39 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
                 if (d > MAXD) {
                     for (int j = 0; j < d; ++j) hb ^= __ldcg(hbit + (size_t)(e0 + j) * kLanes + lane);
                     if (!last) check_generic<NW, AMIN, HLIM>(msg, (size_t)e0, d, lane, skip, tb, kc);
-                } else {
+                } else if (d > 0) {
                     const HB* sh = reinterpret_cast<const HB*>(sb + kMsgBytes);
 #pragma unroll
                     for (int j = 0; j < MAXD; ++j)
-                        if (j < d) hb ^= sh[j * kLanes + lane];
+                        if (j < d - 2 || (j == d - 2 && !fuse_prev) || (j == d - 1 && !fuse_next)) hb ^= sh[j * kLanes + lane];
+                    uint32_t cold_cur = 0;
+                    if (fuse_next) cold_cur = reinterpret_cast<const HB*>(sb + kCbitOff)[lane];
+                    if (fuse_prev) hb ^= cold_prev;
+                    hb ^= cold_cur;
+                    cold_prev = cold_cur;
                     if (!last) {
-                        Lane<NW> x[MAXD];
+                        Lane<NW> x[MAXD], inl;
                         const Lane<NW>* sx = reinterpret_cast<const Lane<NW>*>(sb);
 #pragma unroll
                         for (int j = 0; j < MAXD; ++j)
                             if (j < d) x[j] = sx[j * kLanes + lane];
+                        if (fuse_prev) inl = reinterpret_cast<const Lane<NW>*>(sb + kInqOff)[lane];
+                        HB* cn = cnew + (size_t)(r > 0 ? r - 1 : 0) * kLanes;
+#define LDPC_CHECK_CASE(D_) \
+    case D_: check_fixed<NW, MAXD, (D_ <= MAXD ? D_ : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc, fuse_prev, fuse_next, carry, inl, jones, cn); break;
                         switch (d) {
-                            case 2: check_fixed<NW, MAXD, 2, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
-                            case 3: check_fixed<NW, MAXD, 3, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
-                            case 4: check_fixed<NW, MAXD, 4, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
-                            case 5: check_fixed<NW, MAXD, 5, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
-                            case 6: check_fixed<NW, MAXD, 6, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
-                            case 7: check_fixed<NW, MAXD, 7, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
-                            case 8: check_fixed<NW, MAXD, 8, AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
-                            case 9: if (MAXD >= 9) check_fixed<NW, MAXD, (MAXD >= 9 ? 9 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
-                            case 10: if (MAXD >= 10) check_fixed<NW, MAXD, (MAXD >= 10 ? 10 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc); break;
-                            default: break;   // degree 0; degree 1 is refused before launch (reference panics)
+                            LDPC_CHECK_CASE(2) LDPC_CHECK_CASE(3) LDPC_CHECK_CASE(4) LDPC_CHECK_CASE(5) LDPC_CHECK_CASE(6)
+                            LDPC_CHECK_CASE(7) LDPC_CHECK_CASE(8)
+                            case 9: if (MAXD >= 9) { check_fixed<NW, MAXD, (MAXD >= 9 ? 9 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc, false, false, carry, inl, jones, cn); } break;
+                            case 10: if (MAXD >= 10) { check_fixed<NW, MAXD, (MAXD >= 10 ? 10 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc, false, false, carry, inl, jones, cn); } break;
+                            default: break;   // degree 1 is refused before launch (the reference panics)
                         }
+#undef LDPC_CHECK_CASE
                     }
                 }
                 synd |= hb;
                 __syncwarp();          // every lane is done with this stage before it is refilled
+                r = rn;
             }
         }
         if (synd) atomicOr(&s_unsat[lane], synd);
@@ -695,7 +754,9 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
                     size_t o = (size_t)v * kLanes + lane;
                     int p0 = __ldg(g.col_ptr + v), p1 = __ldg(g.col_ptr + v + 1);
                     uint32_t hb;
-                    if (p1 > p0) hb = __ldcg(hbit + (size_t)__ldg(g.col_edge + p0) * kLanes + lane);
+                    const int fr = __ldg(p.fused_row + v);
+                    if (fr >= 0) hb = __ldcg(cbit + ((size_t)((it - 1) & 1) * g.m + fr) * kLanes + lane);      // fused variable: decisions of iteration it-1
+                    else if (p1 > p0) hb = __ldcg(hbit + (size_t)__ldg(g.col_edge + p0) * kLanes + lane);
                     else if (it == 1) hb = raw0[o];
                     else {                            // isolated variable: posterior = quantised input
                         hb = 0;
@@ -723,7 +784,6 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
         PROF_ADD(2, pt_c1, pt_v0);
         } else {
         PROF_T(pt_v0);
-        const bool jones = p.jones != 0, d1c = p.deg1clip != 0;
         const uint32_t vskip = s_skip;
         for (int k = 0; k < p.vc.num_classes; ++k) {
             const int deg = p.vc.deg[k], off = p.vc.off[k], cnt = p.vc.off[k + 1] - off;
@@ -770,7 +830,8 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
 template <int NW, bool AMIN, bool HLIM>
 void launch_one(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t stream) {
     constexpr int MAXD = NW == 1 ? 10 : 8;
-    constexpr size_t stage = (size_t)MAXD * kLanes * NW * 4 + (size_t)MAXD * kLanes * sizeof(typename HBitsT<NW>::type);
+    constexpr size_t stage = (size_t)MAXD * kLanes * NW * 4 + (size_t)MAXD * kLanes * sizeof(typename HBitsT<NW>::type) +
+                             (size_t)kLanes * NW * 4 + (size_t)kLanes * sizeof(typename HBitsT<NW>::type);
     constexpr size_t smem = (size_t)kGroups * kWarps * 2 * stage;
     // per device and cheap: set on every launch (one process may drive several GPUs)
     cudaFuncSetAttribute(flood_i8_kernel<NW, AMIN, HLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -816,6 +877,7 @@ bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream) {
     FloodI8Params p;
     p.g = L.graph; p.vc = L.classes;
     p.msg = L.msg; p.hbit = L.hbit; p.inq = L.inq; p.raw0 = L.raw0; p.final_hard = L.final_hard; p.iters = L.iters;
+    p.row_meta = L.row_meta; p.fused_row = L.fused_row; p.cbit = L.cbit;
     p.max_iter = L.max_iter; p.num_tiles = L.num_tiles; p.jones = L.jones; p.deg1clip = L.deg1clip;
     p.c_m1 = -1; p.c_one = 1; p.c_m2 = -2; p.c_ff = 0xff; p.c_sh8 = 1 << 8; p.c_sh16 = 1 << 16; p.c_sh24 = 1 << 24;
     if (L.words_per_lane == 4) launch_nw<4>(L, p, stream);

@@ -104,7 +104,25 @@ __global__ void __launch_bounds__(256) emit_kernel(EmitLaunch p) {
     }
 }
 
+template <class F>
+__global__ void emit_posteriors_kernel(const F* __restrict__ post, int n, size_t nframes, double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;          // one thread per (frame, variable)
+    if (i >= nframes * (size_t)n) return;
+    const size_t frame = i / (size_t)n, v = i % (size_t)n;
+    out[i] = (double)post[((frame / kTileFrames) * (size_t)n + v) * kTileFrames + frame % kTileFrames];
+}
+
 }  // namespace
+
+bool launch_emit_posteriors(const void* post_tiles, bool is_f64, int n, size_t nframes, double* out, cudaStream_t stream) {
+    const size_t total = nframes * (size_t)n;
+    if (total == 0) return true;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (is_f64) emit_posteriors_kernel<double><<<blocks, 256, 0, stream>>>(static_cast<const double*>(post_tiles), n, nframes, out);
+    else emit_posteriors_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(post_tiles), n, nframes, out);
+    LDPC_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
 
 bool launch_ingest(const IngestLaunch& L, cudaStream_t stream) {
     if (L.num_tiles == 0 || L.n == 0) return true;

@@ -41,6 +41,7 @@ struct SmemLayeredParams {
     size_t out_len, out_stride;
     int32_t* iters;
     int max_iter;
+    double* post;            // test hook (may be null): [nframes][n] Qv when the frame ended (horizontal_layered.rs:65-88)
 };
 
 template <class T> __device__ __forceinline__ T ld_cs(const T* p) { return __ldcs(p); }
@@ -185,6 +186,8 @@ __global__ void __launch_bounds__(kSmemLayeredMaxThreads, sizeof(F) == 8 ? 1 : 2
         }
     }
     if (tid == 0) p.iters[frame] = result;
+    if (p.post)
+        for (int v = tid; v < g.n; v += T) p.post[frame * (size_t)g.n + v] = (double)qs[v];
     for (size_t v = tid; v < p.out_len; v += T)
         p.out[frame * p.out_stride + v] = (uint8_t)(from_raw ? hard_raw((int)v) : hard_q((int)v));
 }
@@ -197,6 +200,7 @@ bool launch_t(const LayeredSmemLaunch& L, cudaStream_t stream) {
     p.g = L.graph; p.llrs = L.llrs; p.in_f64 = L.in_f64 ? 1 : 0; p.llrs_len = L.llrs_len; p.src_map = L.src_map;
     p.rcv = static_cast<R*>(L.rcv); p.out = L.out; p.out_len = L.out_len; p.out_stride = L.out_stride; p.iters = L.iters;
     p.max_iter = L.max_iter;
+    p.post = L.post;
     const size_t smem = layered_smem_bytes(L.graph.n, L.is_f64, L.is_i8);
     // per device and cheap: set on every launch (one process may drive several GPUs)
     LDPC_CUDA_CHECK(cudaFuncSetAttribute(layered_smem_kernel<F, RULE, IS_I8, HLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

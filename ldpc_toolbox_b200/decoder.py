@@ -86,6 +86,24 @@ class Decoder:
             raise ValueError(f"decode_batch: {capi.last_error()}")
         return out, iterations
 
+    def decode_batch_posteriors(self, llrs, max_iterations: int, output_len: int | None = None):
+        """Test hook (float decoders): (hard words, iterations, posterior LLRs [nframes][n] as f64)."""
+        llrs = np.ascontiguousarray(llrs)
+        if llrs.dtype != np.float32:
+            llrs = llrs.astype(np.float64, copy=False)
+        nframes, per = llrs.shape
+        output_len = self.n if output_len is None else output_len
+        out = np.zeros((nframes, output_len), dtype=np.uint8)
+        iterations = np.zeros(nframes, dtype=np.int32)
+        post = np.zeros((nframes, self.n), dtype=np.float64)
+        fn = (self._lib.ldpc_toolbox_decoder_decode_batch_posteriors_f32 if llrs.dtype == np.float32
+              else self._lib.ldpc_toolbox_decoder_decode_batch_posteriors_f64)
+        rc = fn(self._h, out.ctypes.data, output_len, out.strides[0], llrs.ctypes.data, per, nframes, max_iterations,
+                iterations.ctypes.data, post.ctypes.data)
+        if rc != 0:
+            raise ValueError(f"decode_batch_posteriors: {capi.last_error()}")
+        return out, iterations, post
+
     def decode_batch_ptr(self, llrs_ptr: int, is_f64: bool, llrs_len: int, nframes: int, max_iterations: int,
                          out_ptr: int, output_len: int, output_stride: int, iters_ptr: int, device: bool, stream: int = 0):
         """Raw-pointer call (host or device buffers), used with torch pinned / CUDA tensors."""
@@ -97,6 +115,19 @@ class Decoder:
             rc = fn(self._h, out_ptr, output_len, output_stride, llrs_ptr, llrs_len, nframes, max_iterations, iters_ptr)
         if rc != 0:
             raise ValueError(f"decode_batch: {capi.last_error()}")
+
+    def submit_batch_ptr(self, llrs_ptr: int, is_f64: bool, llrs_len: int, nframes: int, max_iterations: int,
+                         out_ptr: int, output_len: int, output_stride: int, iters_ptr: int) -> int:
+        """Asynchronous host-buffer decode (pinned buffers): returns a ticket for wait()."""
+        fn = self._lib.ldpc_toolbox_decoder_submit_batch_f64 if is_f64 else self._lib.ldpc_toolbox_decoder_submit_batch_f32
+        t = fn(self._h, out_ptr, output_len, output_stride, llrs_ptr, llrs_len, nframes, max_iterations, iters_ptr)
+        if t < 0:
+            raise ValueError(f"submit_batch: {capi.last_error()}")
+        return int(t)
+
+    def wait(self, ticket: int) -> None:
+        if self._lib.ldpc_toolbox_decoder_wait(self._h, ticket) != 0:
+            raise RuntimeError(f"wait: {capi.last_error()}")
 
     def last_timing(self):
         ms = (C.c_float * 3)()

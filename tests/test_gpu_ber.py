@@ -52,6 +52,30 @@ def test_dump_consistency(oracle, spec, impl, punct, ebn0):
     assert abs(msg.mean() - 0.5) < 5 * 0.5 / math.sqrt(msg.size)
 
 
+@pytest.mark.parametrize("bch_max_errors", [1, 3])
+def test_bch_threshold_counters(bch_max_errors):
+    """reference src/simulation/ber.rs:328-337: a frame with at most bch_max_errors info-bit errors counts as
+    corrected by the outer BCH code (its iterations go to bch.correct_iterations), the others add their bit
+    errors and one frame error.  DVB-S2 short r=1/2 near the waterfall leaves many frames with 1-3 bit errors."""
+    eng = BerEngine(codes.alist_for("dvbs2:R1_2short"), "Minstarapproxi8")
+    nframes, max_iter = 3000, 12
+    counters, llrs, dec, its, msg = eng.run_dump(1.45, max_iter, first_frame=500, nframes=nframes, bch_max_errors=bch_max_errors)
+    be = (dec != msg).sum(axis=1)
+    iters = np.where(its < 0, max_iter, its)
+    hard = be > bch_max_errors
+    assert ((be > 0) & ~hard).sum() >= 5, "the point must produce frames the BCH threshold corrects"
+    assert hard.sum() >= 5
+    assert counters["bch_bit_errors"] == be[hard].sum()
+    assert counters["bch_frame_errors"] == hard.sum()
+    assert counters["bch_correct_iterations"] == iters[~hard].sum()
+    assert counters["frame_errors"] == (be > 0).sum() and counters["bit_errors"] == be.sum()
+    assert counters["correct_iterations"] == iters[be == 0].sum()
+    # the driver stops on the BCH frame errors when the threshold is active (ber.rs:514-520)
+    t = BerTest([eng], eng.k, [1.45], max_iterations=max_iter, max_frame_errors=40, bch_max_errors=bch_max_errors, batch=1024)
+    st = t.run()[0]
+    assert st.bch is not None and st.bch.frame_errors >= 40 and st.ldpc.frame_errors > st.bch.frame_errors
+
+
 def test_sharding_invariance_and_determinism():
     alist = codes.alist_for("dvbs2:R1_2short")
     eng = BerEngine(alist, "Minstarapproxi8")

@@ -1,5 +1,8 @@
 """GPU parity: the CUDA flooding i8 decoders (K1) against the CPU checker, through the C-ABI,
 bit-exact on decoded words AND iteration counts (BASELINE.json north_star).  Needs a B200."""
+import os
+import zlib
+
 import numpy as np
 import pytest
 
@@ -80,6 +83,59 @@ def test_512_frame_tiles(oracle, impl, monkeypatch):
     msgs, cws = helpers.encoded_frames(enc, rng, k, 16200, 64)
     llrs = helpers.awgn_llrs(rng, cws, helpers.sigma_for(1.0, k / 16200))
     compare(oracle, alist, impl, llrs, 20, out_len=k, label="nw4 dvbs2 short ")
+
+
+@pytest.mark.parametrize("nw", ["1", "4"])
+@pytest.mark.parametrize("impl", I8_FLOOD)
+def test_staircase_fusion(oracle, impl, nw, monkeypatch):
+    """IRA codes (H = [H0 | staircase]): the degree-2 parity variables are updated inside the check pass
+    (decoder_impl.hpp RowMeta).  Row degrees 2..10 and 14 mix fused rows, rows on the register path that
+    cannot fuse (degree > 8), generic-degree rows and chunk boundaries (m not a multiple of 32); LDPC_B200_FUSE=0
+    must give the same answer through the ordinary variable pass."""
+    monkeypatch.setenv("LDPC_B200_NW", nw)
+    rng = np.random.default_rng(zlib.crc32(impl.encode()) + int(nw))
+    for trial, (k, m, heavy) in enumerate([(90, 70, ()), (150, 101, (5, 40)), (40, 33, ())]):
+        alist = helpers.random_ira_alist(rng, k, m, heavy_rows=heavy)
+        enc = oracle.encoder(alist)
+        nframes = [300, 600, 130][trial]
+        msgs, cws = helpers.encoded_frames(enc, rng, k, k + m, 16)
+        llrs = np.concatenate([helpers.awgn_llrs(rng, cws[np.arange(nframes // 3) % 16], s) for s in (0.45, 0.7, 1.0)])
+        its = compare(oracle, alist, impl, llrs, 14, label=f"ira trial {trial} nw {nw} ")
+        assert (its > 0).any()
+        if trial == 1:
+            monkeypatch.setenv("LDPC_B200_FUSE", "0")
+            compare(oracle, alist, impl, llrs, 14, label=f"ira unfused nw {nw} ")
+            monkeypatch.delenv("LDPC_B200_FUSE")
+
+
+def test_two_lane_pipeline_and_submit_wait(oracle):
+    """Host-buffer batches larger than half a GPU-filling launch are cut into half-launch chunks that alternate
+    between two compute streams / workspaces (decoder.cu submit_batch); consecutive submits share the pipeline.
+    Every frame must come out as from the checker, in place, for ragged tails and for interleaved tickets."""
+    import torch
+    rng = np.random.default_rng(123)
+    alist = helpers.random_ira_alist(rng, 60, 36)
+    n = 96
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    nframes = sm * 512 * 2 + 300                      # two half-launch chunks + a ragged third
+    enc = oracle.encoder(alist)
+    msgs, cws = helpers.encoded_frames(enc, rng, 60, n, 32)
+    llrs = np.concatenate([helpers.awgn_llrs(rng, cws[np.arange(nframes // 2 + 1) % 32], s) for s in (0.6, 0.9)])[:nframes]
+    rout, rits = oracle.decoder(alist, "Minstarapproxi8").decode_batch(llrs, 12, nthreads=os.cpu_count())
+    dec = Decoder(alist, "Minstarapproxi8")
+    out, its = dec.decode_batch(llrs, 12)
+    assert (its == rits).all() and (out == rout).all()
+    # three tickets in flight over pinned buffers, waited out of order
+    h_llrs = torch.from_numpy(llrs).pin_memory()
+    h_out = torch.zeros((nframes, n), dtype=torch.uint8).pin_memory()
+    h_it = torch.zeros(nframes, dtype=torch.int32).pin_memory()
+    cuts = [0, sm * 512 + 77, sm * 512 + 78, nframes]
+    tickets = []
+    for a, b in zip(cuts, cuts[1:]):
+        tickets.append(dec.submit_batch_ptr(h_llrs[a:].data_ptr(), False, n, b - a, 12, h_out[a:].data_ptr(), n, n, h_it[a:].data_ptr()))
+    dec.wait(tickets[-1])
+    dec.wait(tickets[0])
+    assert (h_it.numpy() == rits).all() and (h_out.numpy() == rout).all()
 
 
 def test_ragged_batch_and_strides(oracle):

@@ -6,6 +6,7 @@ tile on DVB-S2 n=64800 r=1/2 — on >= 16 384 frames spread over an Eb/N0 sweep 
 never converge, late and early convergers.  The checker decodes ~140 frames/s on
 16 cores, so this file takes a few minutes of host time.  Needs a B200."""
 import os
+import zlib
 
 import numpy as np
 import pytest
@@ -39,10 +40,10 @@ def test_north_star_bench_kernel_shape_16k_frames(oracle, monkeypatch):
     """BASELINE configs[2], the exact kernel instantiation and launch shape of bench.py: NW = 4 (512-frame
     tiles), cluster of one CTA per tile; then the same frames with the automatic cluster size."""
     alist = codes.alist_for("dvbs2:R1_2")
-    ebn0s = [0.6, 0.7, 0.8, 0.9, 1.0, 1.05, 1.1, 1.15, 1.2, 1.25, 1.3, 1.35, 1.4, 1.5, 1.6, 2.2]
+    ebn0s = [0.6, 0.8, 0.9, 1.0, 1.05, 1.1, 1.15, 1.2, 1.25, 1.3, 1.35, 1.4, 1.5, 1.6, 2.2, 3.0]
     llrs, k = _sweep_llrs(oracle, alist, 16384, ebn0s, seed=2027)
     rout, rits = oracle.decoder(alist, "Minstarapproxi8").decode_batch(llrs, 25, out_len=k, nthreads=os.cpu_count())
-    assert (rits == -1).sum() > 1000 and ((rits > 0) & (rits < 12)).sum() > 500 and (rits >= 18).sum() > 500, \
+    assert (rits == -1).sum() > 1000 and ((rits > 0) & (rits < 13)).sum() > 500 and (rits >= 18).sum() > 500, \
         "the sweep must contain failures, early and late convergers"
     monkeypatch.setenv("LDPC_B200_NW", "4")
     for cluster in ("1", None):
@@ -78,7 +79,7 @@ def test_float_words_at_scale(oracle, code, impl, ebn0, max_iter, frames, allowe
     alist = codes.alist_for(code)
     punct = "1,1,1,1,0" if code.startswith("ar4ja") else ""
     n, k = _dims(alist)
-    rng = np.random.default_rng(abs(hash((code, impl))) % 2**32)
+    rng = np.random.default_rng(zlib.crc32(f"{code}/{impl}".encode()))
     enc = oracle.encoder(alist, punct)
     n_tx = n * 4 // 5 if punct else n
     msgs = rng.integers(0, 2, size=(32, k), dtype=np.uint8)

@@ -264,3 +264,60 @@ def test_cli_encode_and_code_generators(tmp_path, oracle, capsys):
     enc = oracle.encoder(text, "1,1,1,1,0")
     for m, o in zip(msgs, out):
         assert (o[:2048] == enc.encode(m, 2048)).all() and not o[2048:].any()
+
+
+REFERENCE_SYMBOLS = ("ldpc_toolbox_decoder_ctor", "ldpc_toolbox_decoder_ctor_alist_string", "ldpc_toolbox_decoder_dtor",
+                     "ldpc_toolbox_decoder_decode_f64", "ldpc_toolbox_decoder_decode_f32", "ldpc_toolbox_encoder_ctor",
+                     "ldpc_toolbox_encoder_ctor_alist_string", "ldpc_toolbox_encoder_dtor", "ldpc_toolbox_encoder_encode")
+
+
+def test_static_library_links_a_stock_c_program(tmp_path):
+    """Cargo.toml:17-19 builds cdylib + staticlib.  libldpc_toolbox.a must define the reference's nine symbols and a
+    C program written against the REFERENCE header only must link against it (link check; running needs a GPU)."""
+    import subprocess
+    from ldpc_toolbox_b200 import build as b
+    b.build()
+    assert os.path.exists(b.STATIC_LIB)
+    syms = subprocess.run(["nm", "-g", "--defined-only", b.STATIC_LIB], capture_output=True, text=True).stdout
+    for name in REFERENCE_SYMBOLS:
+        assert f" T {name}\n" in syms, name
+    src = tmp_path / "stock.c"
+    src.write_text("""
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+void *ldpc_toolbox_decoder_ctor(const char *alist_file_path, const char *implementation, const char *puncturing);
+void *ldpc_toolbox_decoder_ctor_alist_string(const char *alist, const char *implementation, const char *puncturing);
+void ldpc_toolbox_decoder_dtor(void *decoder);
+int32_t ldpc_toolbox_decoder_decode_f64(void *decoder, uint8_t *output, size_t output_len, const double *llrs, size_t llrs_len, uint32_t max_iterations);
+int32_t ldpc_toolbox_decoder_decode_f32(void *decoder, uint8_t *output, size_t output_len, const float *llrs, size_t llrs_len, uint32_t max_iterations);
+void *ldpc_toolbox_encoder_ctor(const char *alist_file_path, const char *puncturing);
+void *ldpc_toolbox_encoder_ctor_alist_string(const char *alist, const char *puncturing);
+void ldpc_toolbox_encoder_dtor(void *encoder);
+void ldpc_toolbox_encoder_encode(void *encoder, uint8_t *output, size_t output_len, const uint8_t *input, size_t input_len);
+int main(int argc, char **argv) {
+    void *d = ldpc_toolbox_decoder_ctor(argc > 1 ? argv[1] : "x.alist", "Minstarapproxi8", "");
+    if (!d) { puts("NULL"); return 3; }
+    float llrs[6] = {1, 1, -1, 1, -1, -1};
+    uint8_t out[6];
+    int32_t it = ldpc_toolbox_decoder_decode_f32(d, out, 6, llrs, 6, 10);
+    printf("%d\\n", it);
+    ldpc_toolbox_decoder_dtor(d);
+    return 0;
+}
+""")
+    exe = tmp_path / "stock"
+    cudalib = "/usr/local/cuda/lib64"
+    r = subprocess.run(["g++", "-x", "c", str(src), "-x", "none", b.STATIC_LIB, "-L" + cudalib, "-lcudart", "-lpthread", "-ldl", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    # without a GPU the constructor must return NULL (no CPU fallback), with one the program decodes
+    env = dict(os.environ, LD_LIBRARY_PATH=cudalib + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    alist = tmp_path / "j.alist"
+    alist.write_text("6 4\n2 3\n2 2 2 2 2 2\n3 3 3 3\n1 3\n1 2\n2 4\n1 4\n2 3\n3 4\n1 2 4\n2 3 5\n1 5 6\n3 4 6\n")
+    run = subprocess.run([str(exe), str(alist)], capture_output=True, text=True, env=env)
+    import torch
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and run.stdout.strip() == "0"
+    else:
+        assert run.returncode == 3 and run.stdout.strip() == "NULL"
