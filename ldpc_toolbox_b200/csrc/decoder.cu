@@ -410,24 +410,35 @@ private:
     }
 
     // Staircase variables (decoder_impl.hpp, RowMeta): degree 2, last slot of row r and second-to-last slot of
-    // row r+1, both rows inside one chunk of kFuseChunkRows rows and short enough for K1's register path.
+    // row r+1, both rows inside one chunk of chunk_rows_ rows and short enough for K1's register path.
     bool build_row_meta() {
         std::vector<RowMeta> meta((size_t)g_.m);
         std::vector<int> fused_row((size_t)g_.n, -1);
         auto deg_of = [&](int v) { return g_.col_ptr[(size_t)v + 1] - g_.col_ptr[(size_t)v]; };
         auto row_deg = [&](int r) { return g_.row_ptr[(size_t)r + 1] - g_.row_ptr[(size_t)r]; };
         const bool enable = !(getenv("LDPC_B200_FUSE") && atoi(getenv("LDPC_B200_FUSE")) == 0);
+        chunk_rows_ = kFuseChunkRowsDefault;
+        if (const char* e = getenv("LDPC_B200_FUSE_CHUNK")) {
+            const int c = atoi(e);
+            if (c >= 1 && c <= 4096 && (c & (c - 1)) == 0) chunk_rows_ = c;
+        }
         num_fused_ = 0;
         for (int r = 0; r < g_.m; ++r) {
             const int d = row_deg(r);
             meta[(size_t)r] = RowMeta{g_.row_ptr[(size_t)r], d & 0xffff, -1, d > 0 ? g_.col_idx[(size_t)g_.row_ptr[(size_t)r + 1] - 1] : -1};
         }
+        // the kernel addresses the channel LLRs of a fused variable as (row + constant): take the offset of the first
+        // candidate (k - 1 for a staircase code) and leave variables that do not follow it to the variable pass
+        bool have_off = false;
+        fuse_var_off_ = 0;
         for (int r = 0; enable && r + 1 < g_.m; ++r) {
             const int d0 = row_deg(r), d1 = row_deg(r + 1);
-            if ((r + 1) % kFuseChunkRows == 0 || d0 < 2 || d1 < 2 || d0 > kFuseMaxRowDeg || d1 > kFuseMaxRowDeg) continue;
+            if ((r + 1) % chunk_rows_ == 0 || d0 < 2 || d1 < 2 || d0 > kFuseMaxRowDeg || d1 > kFuseMaxRowDeg) continue;
             const int v = g_.col_idx[(size_t)g_.row_ptr[(size_t)r + 1] - 1];
             if (deg_of(v) != 2 || g_.col_idx[(size_t)g_.row_ptr[(size_t)r + 2] - 2] != v) continue;
             if (d0 == 2 && (meta[(size_t)r].d_flags >> 16 & 1) && g_.col_idx[(size_t)g_.row_ptr[(size_t)r]] == v) continue;   // cannot be both slots of row r
+            if (!have_off) { fuse_var_off_ = v - (r + 1); have_off = true; }
+            if (v != r + 1 + fuse_var_off_) continue;
             meta[(size_t)r].d_flags |= 1 << 17;
             meta[(size_t)r + 1].d_flags |= 1 << 16;
             meta[(size_t)r + 1].fuse_var = v;
@@ -605,7 +616,7 @@ private:
             fl.graph = dg_; fl.classes = vc_; fl.num_tiles = tiles; fl.words_per_lane = nw;
             fl.msg = reinterpret_cast<uint32_t*>(ws.msg.p); fl.hbit = ws.hbit.p; fl.inq = reinterpret_cast<const uint32_t*>(ws.inq.p);
             fl.raw0 = ws.hard.p; fl.final_hard = ws.final_hard.p; fl.iters = ws.iters_tile.p; fl.max_iter = max_iter;
-            fl.row_meta = d_row_meta_.p; fl.fused_row = d_fused_row_.p; fl.cbit = ws.cbit.p;
+            fl.row_meta = d_row_meta_.p; fl.fused_row = d_fused_row_.p; fl.cbit = ws.cbit.p; fl.chunk_rows = chunk_rows_; fl.fuse_var_off = fuse_var_off_;
             fl.aminstar = impl_.rule == Rule::Aminstar; fl.jones = impl_.jones; fl.hardlimit = impl_.hardlimit; fl.deg1clip = impl_.deg1clip;
             fl.cluster = 1;
             while (fl.cluster < 16 && tiles * fl.cluster * 2 <= 2 * sm_count_) fl.cluster *= 2;     // up to ~2 CTAs per SM
@@ -754,7 +765,7 @@ private:
     DevBuf<RowMeta> d_row_meta_;
     DevBuf<int> d_fused_row_;
     std::vector<int> h_fused_row_;
-    int num_fused_ = 0;
+    int num_fused_ = 0, chunk_rows_ = kFuseChunkRowsDefault, fuse_var_off_ = 0;
     VarClasses vc_{};
     int num_levels_ = 0;
     bool use_smem_layered_ = false;

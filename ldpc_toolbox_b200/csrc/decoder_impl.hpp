@@ -65,14 +65,14 @@ struct VarClasses {
 // inside the check pass, right after both of its incoming messages of the iteration exist, by the warp that
 // owns both rows; its messages then cross HBM twice per iteration instead of four times.  Exact under
 // flooding: the variable update of iteration i depends only on the two check outputs of iteration i.
-// Rows are dealt to warps in chunks of kFuseChunkRows consecutive rows; a staircase variable that straddles
+// Rows are dealt to warps in chunks of chunk_rows consecutive rows; a staircase variable that straddles
 // two chunks stays in the ordinary variable pass.
-constexpr int kFuseChunkRows = 32;
+constexpr int kFuseChunkRowsDefault = 32;
 constexpr int kFuseMaxRowDeg = 8;
 struct RowMeta {             // one 16-byte record per check row
     int e0;                  // first row-major edge
     int d_flags;             // bits 0-15 degree, bit 16: slot d-2 is fused with row r-1, bit 17: slot d-1 is fused with row r+1
-    int fuse_var;            // variable of the slot fused with row r-1 (its channel LLR line), or -1
+    int fuse_var;            // variable of the slot fused with row r-1, or -1 (always r + fuse_var_off: the kernel uses that)
     int last_var;            // variable of the last slot (raw-sign line of the fused variable at start-up)
 };
 struct FloodI8Launch {
@@ -81,6 +81,8 @@ struct FloodI8Launch {
     const RowMeta* row_meta; // m records
     const int* fused_row;    // n entries: row r whose last slot holds the variable when it is fused, else -1
     void* cbit;              // [tiles][2][m][32] hard decisions of the fused variables, by iteration parity (u8 / u16 per lane)
+    int chunk_rows;          // rows per chunk (power of two), the same value the row records were built with
+    int fuse_var_off;        // every fused variable satisfies v = (row of its second check) + fuse_var_off
     int num_tiles;
     int words_per_lane;      // 1 or 4
     uint32_t* msg;

@@ -61,6 +61,8 @@ struct FloodI8Params {
     const RowMeta* row_meta;  // [m]              per-row record: first edge, degree, staircase-fusion flags (decoder_impl.hpp)
     const int* fused_row;     // [n]              row whose last slot holds the variable when it is fused, else -1
     void* cbit;             // [tiles][2][m][32]  hard decisions of the fused variables by iteration parity, 4*NW bits per lane
+    int chunk_rows;         // rows per chunk dealt to a warp in the check pass (power of two)
+    int fuse_var_off;       // the variable fused between rows r-1 and r is r + fuse_var_off (staircase: k - 1)
     int32_t* iters;         // [tiles*128*NW]     iterations, or -1 on failure
     int max_iter;
     int num_tiles;
@@ -98,6 +100,7 @@ __device__ unsigned long long g_i8_prof[8];
 #define PROF_ADD(slot, a, b) do {} while (0)
 #endif
 constexpr int kMaxGenericD = 64;     // larger rows are rejected when the decoder is built
+constexpr int align128(int x) { return (x + 127) & ~127; }
 
 __device__ __forceinline__ int lane_of_thread() { return threadIdx.x & 31; }
 // barriers of one warp group (named barrier 1 + group, kWarps * 32 threads); with one group per CTA they
@@ -396,7 +399,8 @@ __device__ __forceinline__ uint32_t var_message(uint32_t c_ob, uint32_t base_lo,
 template <int NW, int MAXD, int D, bool AMIN, bool HLIM>
 __device__ __forceinline__ void check_fixed(Lane<NW> (&x)[MAXD], uint32_t* __restrict__ msg, size_t e0, int lane, uint32_t skip,
                                             const Tables& tb, const Consts& k, bool fuse_prev, bool fuse_next, Lane<NW>& carry,
-                                            const Lane<NW>& inl, bool jones, typename HBitsT<NW>::type* __restrict__ cnew_prev) {
+                                            const Lane<NW>* __restrict__ s_inl, bool jones, typename HBitsT<NW>::type* __restrict__ cnew,
+                                            int row, Lane<NW>* __restrict__ cslot) {
     if (skip == 0) {
 #pragma unroll
         for (int q = 0; q < NW; ++q) {
@@ -420,8 +424,13 @@ __device__ __forceinline__ void check_fixed(Lane<NW> (&x)[MAXD], uint32_t* __res
         }
     }
     if (fuse_prev) {
+        // everything the fused update needs is fetched here, after the fold: nothing of it is live across check_word
         const VarConsts vk = var_consts(2, jones);
         uint32_t hb = 0;
+        const Lane<NW> inl = s_inl[lane];
+#ifdef LDPC_I8_CARRY_SMEM
+        carry = cslot[lane];
+#endif
 #pragma unroll
         for (int q = 0; q < NW; ++q) {
             VarAcc sum = widen(inl.w[q]);
@@ -434,11 +443,15 @@ __device__ __forceinline__ void check_fixed(Lane<NW> (&x)[MAXD], uint32_t* __res
             x[D - 2].w[q] = var_message(x[D - 2].w[q], blo, bhi, vk.negK, k);
         }
         st_lane<NW>(msg, e0 - 1, lane, carry);            // the previous row's last edge is this row's first edge - 1
-        cnew_prev[lane] = (typename HBitsT<NW>::type)hb;
+        cnew[(size_t)(row - 1) * kLanes + lane] = (typename HBitsT<NW>::type)hb;
     }
 #pragma unroll
     for (int j = 0; j + 1 < D; ++j) st_lane<NW>(msg, e0 + j, lane, x[j]);
+#ifdef LDPC_I8_CARRY_SMEM
+    if (fuse_next) cslot[lane] = x[D - 1];
+#else
     if (fuse_next) carry = x[D - 1];
+#endif
     else st_lane<NW>(msg, e0 + D - 1, lane, x[D - 1]);
 }
 
@@ -547,10 +560,16 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
     constexpr uint32_t kAll = NW == 1 ? 0xfu : 0xffffu;
     constexpr int kFrames = kTileFrames * NW;
     constexpr int kMsgBytes = MAXD * kLanes * NW * 4;                 // one check's message lines
-    constexpr int kInqOff = kMsgBytes + MAXD * kLanes * (int)sizeof(HB);   // channel LLRs of the variable fused with the previous row
-    constexpr int kCbitOff = kInqOff + kLanes * NW * 4;                    // previous hard decisions of the variable fused with the next row
-    constexpr int kStageBytes = kCbitOff + kLanes * (int)sizeof(HB);
-    extern __shared__ __align__(16) uint8_t dsm[];                    // [kGroups * kWarps][2][kStageBytes]
+    // every region of a stage starts on a 128-byte shared-memory row: a 512-byte line read with LDS.128 (and written by
+    // the TMA) then costs 4 wavefronts, not 8 — a stage size of 5184 bytes (64-byte aligned) cost 12 % of the kernel
+    constexpr int kInqOff = align128(kMsgBytes + MAXD * kLanes * (int)sizeof(HB));   // channel LLRs of the variable fused with the previous row
+    constexpr int kCbitOff = align128(kInqOff + kLanes * NW * 4);                    // previous hard decisions of the variable fused with the next row
+#ifdef LDPC_I8_SMALL_STAGE      // experiment: the round-1 stage size (valid with LDPC_B200_FUSE=0 only)
+    constexpr int kStageBytes = align128(kMsgBytes + MAXD * kLanes * (int)sizeof(HB));
+#else
+    constexpr int kStageBytes = align128(kCbitOff + kLanes * (int)sizeof(HB));
+#endif
+    extern __shared__ __align__(128) uint8_t dsm[];                    // [kGroups * kWarps][2][kStageBytes]
     __shared__ __align__(128) Tables tb;
     __shared__ uint32_t s_unsat_g[kGroups][2][kLanes];      // [iteration parity]: no reset race between the CTAs of a cluster
     __shared__ uint32_t s_done_g[kGroups][kLanes];
@@ -650,10 +669,12 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
             uint8_t* wbuf = dsm + (size_t)cta_warp * 2 * kStageBytes;
             const HB* cold = cbit + (size_t)((it - 1) & 1) * g.m * kLanes;      // hard decisions of iteration it-1
             HB* cnew = cbit + (size_t)(it & 1) * g.m * kLanes;                  // ... of iteration it
-            auto next_row = [&](int r) { const int n1 = r + 1; return (n1 % kFuseChunkRows) ? n1 : n1 + (nw - 1) * kFuseChunkRows; };
+            const int chunk = p.chunk_rows;
+            auto next_row = [&](int r) { const int n1 = r + 1; return (n1 & (chunk - 1)) ? n1 : n1 + (nw - 1) * chunk; };
             // the record of the row after next is fetched one step early, so issuing a stage never waits on it
-            auto meta_of = [&](int r) { return __ldg(reinterpret_cast<const int4*>(p.row_meta) + min(r, g.m - 1)); };
-            auto issue = [&](int stage, int r, const int4& mt) {
+            // (first edge, degree | flags): the first half of the 16-byte row record
+            auto meta_of = [&](int r) { return __ldg(reinterpret_cast<const int2*>(p.row_meta) + 2 * (size_t)min(r, g.m - 1)); };
+            auto issue = [&](int stage, int r, const int2& mt) {
                 const int d = mt.y & 0xffff;
                 if (d <= MAXD && d > 0 && lane == 0) {
                     const bool fp = (mt.y >> 16) & 1, fn = (mt.y >> 17) & 1;
@@ -665,25 +686,37 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
                     mbar_expect_tx(&s_bar[cta_warp][stage], mb + hbytes + ib + cb);
                     if (mb) bulk_g2s(sb, msg + (size_t)mt.x * kLanes * NW, mb, &s_bar[cta_warp][stage]);
                     if (hbytes) bulk_g2s(sb + kMsgBytes, hbit + (size_t)mt.x * kLanes, hbytes, &s_bar[cta_warp][stage]);
-                    if (ib) bulk_g2s(sb + kInqOff, inq + (size_t)mt.z * kLanes * NW, ib, &s_bar[cta_warp][stage]);
+                    if (ib) bulk_g2s(sb + kInqOff, inq + (size_t)(r + p.fuse_var_off) * kLanes * NW, ib, &s_bar[cta_warp][stage]);
                     if (cb) bulk_g2s(sb + kCbitOff, cold + (size_t)r * kLanes, cb, &s_bar[cta_warp][stage]);
                 }
             };
-            int r = gw * kFuseChunkRows, stage = 0;
-            int4 mc = make_int4(0, 0, -1, -1), mn = mc;
+            int r = gw * chunk, stage = 0;
+            int2 mc = make_int2(0, 0), mn = mc;
             if (r < g.m) {
                 mc = meta_of(r);
                 mn = meta_of(next_row(r));
                 issue(0, r, mc);
             }
-            Lane<NW> carry;                  // this warp's message to the variable fused with the next row
+            // this warp's message to the variable fused with the next row: registers, or (LDPC_I8_CARRY_SMEM) a per-warp
+            // shared-memory slot, which frees four registers across the fold of the next row
+            Lane<NW>* const cslot = reinterpret_cast<Lane<NW>*>(dsm + (size_t)kGroups * kWarps * 2 * kStageBytes) + (size_t)cta_warp * kLanes;
+#ifdef LDPC_I8_CARRY_SMEM
+            Lane<NW> carry_dummy;
+#define carry carry_dummy
+#else
+            Lane<NW> carry;
 #pragma unroll
             for (int q = 0; q < NW; ++q) carry.w[q] = 0;
+#endif
             uint32_t cold_prev = 0;          // previous-iteration hard decisions of the variable fused with the previous row
             for (; r < g.m; stage ^= 1) {
-                const int4 mt = mc;
+                const int2 mt = mc;
                 const int e0 = mt.x, d = mt.y & 0xffff;
+#ifdef LDPC_I8_NOFUSE_STATIC       // experiment: compile the fusion out (valid with LDPC_B200_FUSE=0 only)
+                const bool fuse_prev = false, fuse_next = false;
+#else
                 const bool fuse_prev = (mt.y >> 16) & 1, fuse_next = (mt.y >> 17) & 1;
+#endif
                 const int rn = next_row(r);
                 mc = mn;
                 if (rn < g.m) {
@@ -710,20 +743,19 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
                     hb ^= cold_cur;
                     cold_prev = cold_cur;
                     if (!last) {
-                        Lane<NW> x[MAXD], inl;
+                        Lane<NW> x[MAXD];
                         const Lane<NW>* sx = reinterpret_cast<const Lane<NW>*>(sb);
+                        const Lane<NW>* inl = reinterpret_cast<const Lane<NW>*>(sb + kInqOff);
 #pragma unroll
                         for (int j = 0; j < MAXD; ++j)
                             if (j < d) x[j] = sx[j * kLanes + lane];
-                        if (fuse_prev) inl = reinterpret_cast<const Lane<NW>*>(sb + kInqOff)[lane];
-                        HB* cn = cnew + (size_t)(r > 0 ? r - 1 : 0) * kLanes;
 #define LDPC_CHECK_CASE(D_) \
-    case D_: check_fixed<NW, MAXD, (D_ <= MAXD ? D_ : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc, fuse_prev, fuse_next, carry, inl, jones, cn); break;
+    case D_: check_fixed<NW, MAXD, (D_ <= MAXD ? D_ : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc, fuse_prev, fuse_next, carry, inl, jones, cnew, r, cslot); break;
                         switch (d) {
                             LDPC_CHECK_CASE(2) LDPC_CHECK_CASE(3) LDPC_CHECK_CASE(4) LDPC_CHECK_CASE(5) LDPC_CHECK_CASE(6)
                             LDPC_CHECK_CASE(7) LDPC_CHECK_CASE(8)
-                            case 9: if (MAXD >= 9) { check_fixed<NW, MAXD, (MAXD >= 9 ? 9 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc, false, false, carry, inl, jones, cn); } break;
-                            case 10: if (MAXD >= 10) { check_fixed<NW, MAXD, (MAXD >= 10 ? 10 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc, false, false, carry, inl, jones, cn); } break;
+                            case 9: if (MAXD >= 9) { check_fixed<NW, MAXD, (MAXD >= 9 ? 9 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc, false, false, carry, inl, jones, cnew, r, cslot); } break;
+                            case 10: if (MAXD >= 10) { check_fixed<NW, MAXD, (MAXD >= 10 ? 10 : 2), AMIN, HLIM>(x, msg, (size_t)e0, lane, skip, tb, kc, false, false, carry, inl, jones, cnew, r, cslot); } break;
                             default: break;   // degree 1 is refused before launch (the reference panics)
                         }
 #undef LDPC_CHECK_CASE
@@ -733,6 +765,9 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
                 __syncwarp();          // every lane is done with this stage before it is refilled
                 r = rn;
             }
+#ifdef LDPC_I8_CARRY_SMEM
+#undef carry
+#endif
         }
         if (synd) atomicOr(&s_unsat[lane], synd);
         pass_sync();
@@ -830,9 +865,13 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
 template <int NW, bool AMIN, bool HLIM>
 void launch_one(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t stream) {
     constexpr int MAXD = NW == 1 ? 10 : 8;
-    constexpr size_t stage = (size_t)MAXD * kLanes * NW * 4 + (size_t)MAXD * kLanes * sizeof(typename HBitsT<NW>::type) +
-                             (size_t)kLanes * NW * 4 + (size_t)kLanes * sizeof(typename HBitsT<NW>::type);
-    constexpr size_t smem = (size_t)kGroups * kWarps * 2 * stage;
+    constexpr int hb = (int)sizeof(typename HBitsT<NW>::type);
+#ifdef LDPC_I8_SMALL_STAGE
+    constexpr size_t stage = (size_t)align128(MAXD * kLanes * NW * 4 + MAXD * kLanes * hb);
+#else
+    constexpr size_t stage = (size_t)align128(align128(align128(MAXD * kLanes * NW * 4 + MAXD * kLanes * hb) + kLanes * NW * 4) + kLanes * hb);
+#endif
+    constexpr size_t smem = (size_t)kGroups * kWarps * (2 * stage + (size_t)kLanes * NW * 4);     // + per-warp carry slot
     // per device and cheap: set on every launch (one process may drive several GPUs)
     cudaFuncSetAttribute(flood_i8_kernel<NW, AMIN, HLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int C = (kGroups == 1 && L.cluster >= 1 && L.cluster <= 16) ? L.cluster : 1;
@@ -877,7 +916,7 @@ bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream) {
     FloodI8Params p;
     p.g = L.graph; p.vc = L.classes;
     p.msg = L.msg; p.hbit = L.hbit; p.inq = L.inq; p.raw0 = L.raw0; p.final_hard = L.final_hard; p.iters = L.iters;
-    p.row_meta = L.row_meta; p.fused_row = L.fused_row; p.cbit = L.cbit;
+    p.row_meta = L.row_meta; p.fused_row = L.fused_row; p.cbit = L.cbit; p.chunk_rows = L.chunk_rows; p.fuse_var_off = L.fuse_var_off;
     p.max_iter = L.max_iter; p.num_tiles = L.num_tiles; p.jones = L.jones; p.deg1clip = L.deg1clip;
     p.c_m1 = -1; p.c_one = 1; p.c_m2 = -2; p.c_ff = 0xff; p.c_sh8 = 1 << 8; p.c_sh16 = 1 << 16; p.c_sh24 = 1 << 24;
     if (L.words_per_lane == 4) launch_nw<4>(L, p, stream);

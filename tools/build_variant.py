@@ -15,13 +15,14 @@ from ldpc_toolbox_b200 import build as B  # noqa: E402
 
 name, defines = sys.argv[1], sys.argv[2:]
 full = "--full" in defines            # all 8 instantiations (parity tests), not only the north-star one
-defines = [d for d in defines if d != "--full"]
+src = next((d[6:] for d in defines if d.startswith("--src=")), "flood_i8.cu")      # another revision of the kernel source, in csrc/
+defines = [d for d in defines if d != "--full" and not d.startswith("--src=")]
 B.build()
 out = os.path.join(B.OUT_DIR, "variants", name)
 os.makedirs(out, exist_ok=True)
 ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
 obj = os.path.join(out, "flood_i8.o")
-cmd = [B._nvcc()] + ccbin + B.NVCC_FLAGS + ([] if full else ["-DLDPC_I8_BENCH_ONLY"]) + defines + ["-x", "cu", "-c", os.path.join(B.CSRC, "flood_i8.cu"), "-o", obj]
+cmd = [B._nvcc()] + ccbin + B.NVCC_FLAGS + ([] if full else ["-DLDPC_I8_BENCH_ONLY"]) + defines + ["-x", "cu", "-c", os.path.join(B.CSRC, src), "-o", obj]
 r = subprocess.run(cmd, capture_output=True, text=True)
 open(os.path.join(out, "build.log"), "w").write(r.stdout + r.stderr)
 if r.returncode:
