@@ -160,6 +160,15 @@ int32_t ldpc_toolbox_ber_set_modulation(void *ber, const char *modulation, int32
 int32_t ldpc_toolbox_ber_run(void *ber, float ebn0_db, uint32_t max_iterations,
                              uint64_t first_frame, uint64_t nframes, uint64_t seed,
                              uint64_t bch_max_errors, uint64_t *counters);
+/* Asynchronous form: submit enqueues one batch (front-end, decode, back-end, counter read-back) and returns a
+ * ticket (>= 0; -2 on error) without waiting; wait(ticket) blocks until that batch is done and ADDS its nine
+ * counters.  At most two tickets may be in flight per engine (two lanes with their own stream, buffers and
+ * decoder workspace), so the caller's stop rule and counter reduction for batch i overlap the kernels of batch
+ * i+1 — the GPU counterpart of the reference's controller thread receiving results while its workers run ahead
+ * (reference src/simulation/ber.rs:312-343).  ldpc_toolbox_ber_run = submit + wait. */
+int64_t ldpc_toolbox_ber_submit(void *ber, float ebn0_db, uint32_t max_iterations, uint64_t first_frame,
+                                uint64_t nframes, uint64_t seed, uint64_t bch_max_errors);
+int32_t ldpc_toolbox_ber_wait(void *ber, int64_t ticket, uint64_t *counters);
 /* test hook: same as ldpc_toolbox_ber_run, also copying out (any pointer may be NULL) the f32
  * LLRs [nframes][n_tx], decoded info bytes [nframes][k], iterations and packed messages */
 int32_t ldpc_toolbox_ber_run_dump(void *ber, float ebn0_db, uint32_t max_iterations,

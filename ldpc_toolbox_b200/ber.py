@@ -67,6 +67,21 @@ class BerEngine:
             raise RuntimeError(f"ldpc_toolbox_ber_run: {capi.last_error()}")
         return counters
 
+    def submit(self, ebn0_db: float, max_iterations: int, first_frame: int, nframes: int, seed: int = 0x5EED, bch_max_errors: int = 0) -> int:
+        """Asynchronous run(): enqueue the batch and return a ticket; at most two may be in flight."""
+        t = self._lib.ldpc_toolbox_ber_submit(self._h, ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors)
+        if t < 0:
+            raise RuntimeError(f"ldpc_toolbox_ber_submit: {capi.last_error()}")
+        return int(t)
+
+    def wait(self, ticket: int, counters: Optional[np.ndarray] = None) -> np.ndarray:
+        """Block until `ticket` is done and add its nine counters."""
+        if counters is None:
+            counters = np.zeros(NUM_COUNTERS, dtype=np.uint64)
+        if self._lib.ldpc_toolbox_ber_wait(self._h, ticket, counters.ctypes.data) != 0:
+            raise RuntimeError(f"ldpc_toolbox_ber_wait: {capi.last_error()}")
+        return counters
+
     def run_dump(self, ebn0_db: float, max_iterations: int, first_frame: int, nframes: int, seed: int = 0x5EED, bch_max_errors: int = 0):
         """Test hook: also returns the LLRs, decoded info bits, iteration counts and messages."""
         counters = np.zeros(NUM_COUNTERS, dtype=np.uint64)
@@ -157,8 +172,24 @@ class BerTest:
         self.max_frames = max_frames
         self.statistics: list[Statistics] = []
 
-    def _one_round(self, ebn0_db: float, launch: int) -> np.ndarray:
+    @property
+    def pipeline_depth(self) -> int:
+        """Rounds kept in flight: 2 when every engine has the asynchronous submit/wait pair, else 1."""
+        return 2 if all(hasattr(e, "submit") and hasattr(e, "wait") for e in self.engines) else 1
+
+    def overshoot_bound(self) -> int:
+        """Frames that may be simulated beyond the round in which the stop rule first holds."""
+        return (self.pipeline_depth - 1) * self.batch * len(self.engines) * self.world
+
+    def _submit_round(self, ebn0_db: float, launch: int):
+        """Enqueue one round on every local engine (asynchronous engines) or run it (blocking ones)."""
         nloc = len(self.engines)
+        if self.pipeline_depth == 2:
+            tickets = []
+            for i, eng in enumerate(self.engines):
+                first, n = frame_range(launch, self.rank * nloc + i, self.world * nloc, self.batch)
+                tickets.append(eng.submit(ebn0_db, self.max_iterations, first, n, self.seed, self.bch_max_errors))
+            return ("tickets", tickets)
         parts = [np.zeros(NUM_COUNTERS, dtype=np.uint64) for _ in range(nloc)]
         errs: list = [None] * nloc
 
@@ -177,6 +208,16 @@ class BerTest:
         for e in errs:
             if e is not None:
                 raise e
+        return ("counters", parts)
+
+    def _collect_round(self, pending) -> np.ndarray:
+        """Wait for a submitted round, sum its counters over the local engines and (multi-rank) over ranks.  With two
+        rounds in flight this host work — and the all-reduce — overlaps the kernels of the next round."""
+        kind, items = pending
+        if kind == "tickets":
+            parts = [eng.wait(t) for eng, t in zip(self.engines, items)]
+        else:
+            parts = items
         total = np.sum(parts, axis=0).astype(np.uint64)
         if self.allreduce is not None:
             # The stop decision must be collective: besides the nine counters, rank 0's clock travels in
@@ -193,21 +234,31 @@ class BerTest:
 
     def run(self) -> list[Statistics]:
         has_bch = self.bch_max_errors > 0
+        depth = self.pipeline_depth
+        frames_per_round = self.batch * len(self.engines) * self.world
         for ebn0_db in self.ebn0s_db:
             counters = np.zeros(NUM_COUNTERS, dtype=np.uint64)
             start = self._start = time.perf_counter()
             self._shared_elapsed = 0.0
-            launch = 0
+            launch, submitted = 0, 0
+            pending: list = []
+            stopping = False
             while True:
                 # multi-rank: rank 0's clock as of the last all-reduce; single process: the local clock
                 elapsed = self._shared_elapsed if self.allreduce is not None else time.perf_counter() - start
                 errors = int(counters[7] if has_bch else counters[2])        # ber.rs:514-520
                 if run_finished(errors, self.max_frame_errors, elapsed, self.min_time, self.max_time):
-                    break
+                    stopping = True
                 if self.max_frames is not None and int(counters[0]) >= self.max_frames:
+                    stopping = True
+                # keep `depth` rounds in flight; once the stop rule holds, rounds already submitted are still collected
+                while not stopping and len(pending) < depth and (self.max_frames is None or submitted < self.max_frames):
+                    pending.append(self._submit_round(ebn0_db, launch))
+                    launch += 1
+                    submitted += frames_per_round
+                if not pending:
                     break
-                counters += self._one_round(ebn0_db, launch)
-                launch += 1
+                counters += self._collect_round(pending.pop(0))
                 if self.reporter:
                     self.reporter(Statistics.from_counters(counters, ebn0_db, self.k, time.perf_counter() - start, has_bch), False)
             st = Statistics.from_counters(counters, ebn0_db, self.k, time.perf_counter() - start, has_bch)

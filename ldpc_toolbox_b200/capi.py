@@ -42,6 +42,8 @@ _SIGS = {
     "ldpc_toolbox_ber_dtor": (None, [C.c_void_p]),
     "ldpc_toolbox_ber_set_modulation": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int32]),
     "ldpc_toolbox_ber_run": (C.c_int32, [C.c_void_p, C.c_float, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "ldpc_toolbox_ber_submit": (C.c_int64, [C.c_void_p, C.c_float, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "ldpc_toolbox_ber_wait": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p]),
     "ldpc_toolbox_ber_run_dump": (C.c_int32, [C.c_void_p, C.c_float, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldpc_toolbox_ber_dims": (None, [C.c_void_p, C.c_void_p]),

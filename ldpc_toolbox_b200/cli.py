@@ -256,8 +256,9 @@ def run_ber(a, out=sys.stdout) -> list[Statistics]:
                for g in range(a.gpus)]
     e0 = engines[0]
     if a.batch <= 0:
-        # aim at ~2 resident 512-frame tiles per SM for big codes, fewer frames for small ones
-        a.batch = 151552 if e0.n_cw >= 32768 else 65536
+        # one 512-frame tile per SM per batch for big codes — two batches are in flight per GPU, which fills the
+        # SMs with two tiles each — fewer frames for small codes
+        a.batch = 75776 if e0.n_cw >= 32768 else 65536
     write_details(out, a, e0.k, e0.n_cw, e0.n, e0.rate)
     files = []
     if a.output_file:
@@ -294,6 +295,10 @@ def run_ber(a, out=sys.stdout) -> list[Statistics]:
                    max_frame_errors=a.frame_errors, min_time=a.min_time or 0.0,
                    max_time=a.max_time if a.max_time is not None else float("inf"), bch_max_errors=a.bch_max_errors,
                    batch=a.batch, seed=a.seed, reporter=reporter, max_frames=a.max_frames)
+    if test.pipeline_depth > 1:
+        # the reference's workers also run ahead of the controller's stop rule (ber.rs:312-343); here by whole batches
+        out.write(f"(batches of {a.batch} frames x {a.gpus} GPU(s), {test.pipeline_depth} in flight per GPU: a point may "
+                  f"run up to {test.overshoot_bound()} frames past the stop rule)\n")
     stats = test.run()
     for f, _ in files:
         f.close()

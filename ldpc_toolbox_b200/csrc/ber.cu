@@ -277,9 +277,15 @@ bool dev_upload(T** d, const std::vector<T>& h) {
 }  // namespace
 
 BerEngine::~BerEngine() {
+    cudaSetDevice(device_);
+    cudaDeviceSynchronize();
     cudaFree(d_h0_ptr_); cudaFree(d_h0_idx_); cudaFree(d_g0_); cudaFree(d_kept_);
-    cudaFree(d_llrs_); cudaFree(d_messages_); cudaFree(d_decoded_); cudaFree(d_iters_); cudaFree(d_counters_);
-    if (stream_) cudaStreamDestroy(stream_);
+    for (Lane& ln : lanes_) {
+        cudaFree(ln.d_llrs); cudaFree(ln.d_messages); cudaFree(ln.d_decoded); cudaFree(ln.d_iters); cudaFree(ln.d_counters);
+        if (ln.h_counters) cudaFreeHost(ln.h_counters);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+        if (ln.done) cudaEventDestroy(ln.done);
+    }
 }
 
 std::unique_ptr<BerEngine> BerEngine::create(const Graph& g, const DecoderImplementation& impl, const Puncturer* punct,
@@ -316,8 +322,12 @@ std::unique_ptr<BerEngine> BerEngine::create(const Graph& g, const DecoderImplem
         if (!dev_upload(&e->d_g0_, g0)) return nullptr;
     }
     if (!dev_upload(&e->d_kept_, kept)) return nullptr;
-    if (cudaMalloc(&e->d_counters_, kBerCounters * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
-    if (cudaStreamCreateWithFlags(&e->stream_, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (Lane& ln : e->lanes_) {
+        if (cudaMalloc(&ln.d_counters, kBerCounters * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+        if (cudaMallocHost(&ln.h_counters, kBerCounters * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
     return e;
 }
 
@@ -340,30 +350,29 @@ bool BerEngine::set_modulation(const std::string& name, int interleaving_columns
     return true;
 }
 
-bool BerEngine::ensure(size_t nframes) {
-    if (nframes <= cap_frames_) return true;
-    cudaFree(d_llrs_); cudaFree(d_messages_); cudaFree(d_decoded_); cudaFree(d_iters_);
-    d_llrs_ = nullptr; d_messages_ = nullptr; d_decoded_ = nullptr; d_iters_ = nullptr;
+bool BerEngine::ensure(Lane& ln, size_t nframes) {
+    if (nframes <= ln.cap_frames) return true;
+    cudaStreamSynchronize(ln.stream);
+    cudaFree(ln.d_llrs); cudaFree(ln.d_messages); cudaFree(ln.d_decoded); cudaFree(ln.d_iters);
+    ln.d_llrs = nullptr; ln.d_messages = nullptr; ln.d_decoded = nullptr; ln.d_iters = nullptr;
     const size_t kw = (size_t)(k_ + 31) / 32;
-    if (cudaMalloc(&d_llrs_, nframes * (size_t)n_tx_ * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&d_messages_, nframes * kw * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMalloc(&d_decoded_, std::max<size_t>(nframes * (size_t)k_, 1)) != cudaSuccess ||
-        cudaMalloc(&d_iters_, nframes * sizeof(int32_t)) != cudaSuccess) {
+    if (cudaMalloc(&ln.d_llrs, nframes * (size_t)n_tx_ * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&ln.d_messages, nframes * kw * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&ln.d_decoded, std::max<size_t>(nframes * (size_t)k_, 1)) != cudaSuccess ||
+        cudaMalloc(&ln.d_iters, nframes * sizeof(int32_t)) != cudaSuccess) {
         cudaGetLastError();
         set_last_error("cudaMalloc failed (BER engine buffers)");
-        cap_frames_ = 0;
+        ln.cap_frames = 0;
         return false;
     }
-    cap_frames_ = nframes;
+    ln.cap_frames = nframes;
     return true;
 }
 
-bool BerEngine::run(float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes, uint64_t seed,
-                    uint64_t bch_max_errors, uint64_t* counters, float* dump_llrs, uint8_t* dump_decoded, int32_t* dump_iters,
-                    uint32_t* dump_messages) {
-    LDPC_CUDA_CHECK(cudaSetDevice(device_));
-    if (nframes == 0) return true;
-    if (!ensure((size_t)nframes)) return false;
+// front-end -> decoder -> back-end -> counters to pinned host memory, all asynchronous on the lane's stream
+bool BerEngine::enqueue(Lane& ln, int lane_index, float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes,
+                        uint64_t seed, uint64_t bch_max_errors) {
+    if (!ensure(ln, (size_t)nframes)) return false;
     const double sigma = noise_sigma(ebn0_db);
     FrontendParams fp{};
     fp.n = n_; fp.m = m_; fp.k = k_; fp.n_tx = n_tx_; fp.staircase = plan_.staircase ? 1 : 0;
@@ -375,31 +384,68 @@ bool BerEngine::run(float ebn0_db, uint32_t max_iterations, uint64_t first_frame
     fp.seed_lo = (uint32_t)seed; fp.seed_hi = (uint32_t)(seed >> 32) ^ eb_bits;
     fp.sigma = (float)sigma; fp.llr_scale = (float)(-2.0 / (sigma * sigma));
     fp.modulation = modulation_; fp.il_cols = il_cols_; fp.il_backwards = il_backwards_; fp.sigma_d = sigma;
-    fp.llrs = d_llrs_; fp.messages = d_messages_;
+    fp.llrs = ln.d_llrs; fp.messages = ln.d_messages;
     const size_t smem = ((size_t)(k_ + 31) / 32 + (size_t)(m_ + 31) / 32 + 4) * sizeof(uint32_t);
     if (smem > 48 * 1024) LDPC_CUDA_CHECK(cudaFuncSetAttribute(ber_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LDPC_CUDA_CHECK(cudaMemsetAsync(d_counters_, 0, kBerCounters * sizeof(unsigned long long), stream_));
-    ber_frontend_kernel<<<(unsigned)nframes, 256, smem, stream_>>>(fp);
+    LDPC_CUDA_CHECK(cudaMemsetAsync(ln.d_counters, 0, kBerCounters * sizeof(unsigned long long), ln.stream));
+    ber_frontend_kernel<<<(unsigned)nframes, 256, smem, ln.stream>>>(fp);
     LDPC_CUDA_CHECK(cudaGetLastError());
-    if (!decoder_->decode_batch_device(d_llrs_, false, (size_t)n_tx_, (size_t)nframes, max_iterations, d_decoded_, (size_t)k_, (size_t)k_,
-                                       d_iters_, stream_))
+    if (!decoder_->decode_batch_device_lane(lane_index, ln.d_llrs, false, (size_t)n_tx_, (size_t)nframes, max_iterations, ln.d_decoded, (size_t)k_,
+                                            (size_t)k_, ln.d_iters, ln.stream))
         return false;
     BackendParams bp{};
     bp.k = k_; bp.max_iter = max_iterations; bp.bch_max_errors = bch_max_errors;
-    bp.decoded = d_decoded_; bp.iters = d_iters_; bp.messages = d_messages_; bp.counters = d_counters_;
-    ber_backend_kernel<<<(unsigned)nframes, 256, 0, stream_>>>(bp);
+    bp.decoded = ln.d_decoded; bp.iters = ln.d_iters; bp.messages = ln.d_messages; bp.counters = ln.d_counters;
+    ber_backend_kernel<<<(unsigned)nframes, 256, 0, ln.stream>>>(bp);
     LDPC_CUDA_CHECK(cudaGetLastError());
-    unsigned long long host[kBerCounters];
-    LDPC_CUDA_CHECK(cudaMemcpyAsync(host, d_counters_, sizeof(host), cudaMemcpyDeviceToHost, stream_));
-    if (dump_llrs) LDPC_CUDA_CHECK(cudaMemcpyAsync(dump_llrs, d_llrs_, nframes * (size_t)n_tx_ * sizeof(float), cudaMemcpyDeviceToHost, stream_));
-    if (dump_decoded) LDPC_CUDA_CHECK(cudaMemcpyAsync(dump_decoded, d_decoded_, nframes * (size_t)k_, cudaMemcpyDeviceToHost, stream_));
-    if (dump_iters) LDPC_CUDA_CHECK(cudaMemcpyAsync(dump_iters, d_iters_, nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
-    if (dump_messages)
-        LDPC_CUDA_CHECK(cudaMemcpyAsync(dump_messages, d_messages_, nframes * ((size_t)(k_ + 31) / 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
-    LDPC_CUDA_CHECK(cudaStreamSynchronize(stream_));
-    for (int i = 0; i < kBerCounters; ++i) counters[i] += host[i];
+    LDPC_CUDA_CHECK(cudaMemcpyAsync(ln.h_counters, ln.d_counters, kBerCounters * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ln.stream));
     launches_ += 2 + 3;
     return true;
+}
+
+int64_t BerEngine::submit(float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes, uint64_t seed,
+                          uint64_t bch_max_errors) {
+    if (cudaSetDevice(device_) != cudaSuccess) { set_last_error("cudaSetDevice failed"); return -1; }
+    const int64_t ticket = next_ticket_;
+    Lane& ln = lanes_[ticket & 1];
+    if (ln.ticket >= 0) { set_last_error("BER engine: two batches are already in flight (wait for the older ticket first)"); return -1; }
+    if (nframes > 0) {
+        if (!enqueue(ln, (int)(ticket & 1), ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors)) return -1;
+    } else {
+        memset(ln.h_counters, 0, kBerCounters * sizeof(unsigned long long));
+    }
+    if (cudaEventRecord(ln.done, ln.stream) != cudaSuccess) { set_last_error("cudaEventRecord failed"); return -1; }
+    ln.ticket = ticket;
+    ++next_ticket_;
+    return ticket;
+}
+
+bool BerEngine::wait(int64_t ticket, uint64_t* counters) {
+    if (ticket < 0) { set_last_error("BER engine: bad ticket"); return false; }
+    Lane& ln = lanes_[ticket & 1];
+    if (ln.ticket != ticket) { set_last_error("BER engine: ticket is not in flight"); return false; }
+    ln.ticket = -1;
+    LDPC_CUDA_CHECK(cudaSetDevice(device_));
+    LDPC_CUDA_CHECK(cudaEventSynchronize(ln.done));
+    for (int i = 0; i < kBerCounters; ++i) counters[i] += ln.h_counters[i];
+    return true;
+}
+
+bool BerEngine::run(float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes, uint64_t seed,
+                    uint64_t bch_max_errors, uint64_t* counters, float* dump_llrs, uint8_t* dump_decoded, int32_t* dump_iters,
+                    uint32_t* dump_messages) {
+    if (nframes == 0) return true;
+    const int64_t t = submit(ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors);
+    if (t < 0) return false;
+    Lane& ln = lanes_[t & 1];
+    // test hooks: the lane's buffers are intact until its next submit
+    if (dump_llrs) LDPC_CUDA_CHECK(cudaMemcpyAsync(dump_llrs, ln.d_llrs, nframes * (size_t)n_tx_ * sizeof(float), cudaMemcpyDeviceToHost, ln.stream));
+    if (dump_decoded) LDPC_CUDA_CHECK(cudaMemcpyAsync(dump_decoded, ln.d_decoded, nframes * (size_t)k_, cudaMemcpyDeviceToHost, ln.stream));
+    if (dump_iters) LDPC_CUDA_CHECK(cudaMemcpyAsync(dump_iters, ln.d_iters, nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, ln.stream));
+    if (dump_messages)
+        LDPC_CUDA_CHECK(cudaMemcpyAsync(dump_messages, ln.d_messages, nframes * ((size_t)(k_ + 31) / 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ln.stream));
+    LDPC_CUDA_CHECK(cudaStreamSynchronize(ln.stream));
+    return wait(t, counters);
 }
 
 }  // namespace ldpc

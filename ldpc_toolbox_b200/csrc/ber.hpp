@@ -28,6 +28,14 @@ public:
     bool run(float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes, uint64_t seed,
              uint64_t bch_max_errors, uint64_t* counters, float* dump_llrs = nullptr, uint8_t* dump_decoded = nullptr,
              int32_t* dump_iters = nullptr, uint32_t* dump_messages = nullptr);
+    // Asynchronous form: submit() enqueues front-end, decode, back-end and the read-back of the nine counters on one
+    // of two lanes (own stream, buffers and decoder workspace) and returns a ticket (>= 0, -1 on error) without
+    // waiting; wait(ticket) blocks until that batch is done and ADDS its counters.  Two tickets may be in flight,
+    // so the host's stop rule / counter reduction for batch i overlaps the kernels of batch i+1 (ber.rs:312-343:
+    // the reference's controller also keeps receiving results while the workers run ahead).
+    int64_t submit(float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes, uint64_t seed,
+                   uint64_t bch_max_errors);
+    bool wait(int64_t ticket, uint64_t* counters);
     double noise_sigma(float ebn0_db) const;
     // "BPSK" or "8PSK" (reference src/simulation/factory.rs:56-86); interleaving_columns: 0 = none, n = DVB-S2
     // bit interleaver with n columns, -n = rows read backwards (reference src/simulation/ber.rs:250-252)
@@ -41,17 +49,26 @@ public:
 
 private:
     BerEngine() = default;
-    bool ensure(size_t nframes);
+    struct Lane {
+        float* d_llrs = nullptr; uint32_t* d_messages = nullptr; uint8_t* d_decoded = nullptr; int32_t* d_iters = nullptr;
+        unsigned long long* d_counters = nullptr;
+        unsigned long long* h_counters = nullptr;      // pinned
+        size_t cap_frames = 0;
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        int64_t ticket = -1;                           // ticket in flight on this lane, or -1
+    };
+    bool ensure(Lane& ln, size_t nframes);
+    bool enqueue(Lane& ln, int lane_index, float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes, uint64_t seed,
+                 uint64_t bch_max_errors);
+    Lane lanes_[2];
+    int64_t next_ticket_ = 0;
     EncoderPlan plan_;
     std::unique_ptr<LdpcDecoder> decoder_;
     int n_ = 0, m_ = 0, k_ = 0, n_tx_ = 0, device_ = 0, g0_words_ = 0;
     int modulation_ = 0, il_cols_ = 0, il_backwards_ = 0;
     double rate_ = 0;
     int* d_h0_ptr_ = nullptr; int* d_h0_idx_ = nullptr; uint32_t* d_g0_ = nullptr; int* d_kept_ = nullptr;
-    float* d_llrs_ = nullptr; uint32_t* d_messages_ = nullptr; uint8_t* d_decoded_ = nullptr; int32_t* d_iters_ = nullptr;
-    unsigned long long* d_counters_ = nullptr;
-    size_t cap_frames_ = 0;
-    cudaStream_t stream_ = nullptr;
     long long launches_ = 0;
 };
 

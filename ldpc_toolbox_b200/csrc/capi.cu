@@ -299,6 +299,18 @@ int32_t ldpc_toolbox_ber_run_dump(void* ber, float ebn0_db, uint32_t max_iterati
                                              decoded, iterations, messages) ? 0 : -2;
 }
 
+int64_t ldpc_toolbox_ber_submit(void* ber, float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes, uint64_t seed,
+                                uint64_t bch_max_errors) {
+    if (!ber) return -2;
+    const int64_t t = static_cast<BerEngine*>(ber)->submit(ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors);
+    return t >= 0 ? t : -2;
+}
+
+int32_t ldpc_toolbox_ber_wait(void* ber, int64_t ticket, uint64_t* counters) {
+    if (!ber || !counters) return -2;
+    return static_cast<BerEngine*>(ber)->wait(ticket, counters) ? 0 : -2;
+}
+
 void ldpc_toolbox_ber_dims(void* ber, uint64_t* what3) {
     if (!ber || !what3) return;
     auto* b = static_cast<BerEngine*>(ber);

@@ -300,6 +300,13 @@ public:
     bool decode_batch_device(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nframes, uint32_t max_iterations,
                              uint8_t* d_out, size_t out_len, size_t out_stride, int32_t* d_iterations,
                              cudaStream_t stream) override {
+        return decode_batch_device_lane(0, d_llrs, is_f64, llrs_len, nframes, max_iterations, d_out, out_len, out_stride, d_iterations, stream);
+    }
+
+    bool decode_batch_device_lane(int lane, const void* d_llrs, bool is_f64, size_t llrs_len, size_t nframes, uint32_t max_iterations,
+                                  uint8_t* d_out, size_t out_len, size_t out_stride, int32_t* d_iterations,
+                                  cudaStream_t stream) override {
+        if (lane < 0 || lane > 1) { set_last_error("lane must be 0 or 1"); return false; }
         if (!check_args(llrs_len, out_len, out_stride)) return false;
         if (nframes == 0) return true;
         DeviceScope scope(device_);
@@ -308,7 +315,7 @@ public:
         const size_t chunk_frames = plan_chunk_frames(nframes, 0);
         for (size_t f0 = 0; f0 < nframes; f0 += chunk_frames) {
             size_t nf = std::min(chunk_frames, nframes - f0);
-            if (!run_chunk(ws_[0], (const uint8_t*)d_llrs + f0 * llrs_len * esz, is_f64, llrs_len, nf, max_iterations,
+            if (!run_chunk(ws_[lane], (const uint8_t*)d_llrs + f0 * llrs_len * esz, is_f64, llrs_len, nf, max_iterations,
                            d_out + f0 * out_stride, out_len, out_stride, d_iterations + f0, stream))
                 return false;
         }

@@ -54,6 +54,11 @@ public:
     virtual bool decode_batch_device(const void* d_llrs, bool is_f64, size_t llrs_len, size_t nframes,
                                      uint32_t max_iterations, uint8_t* d_out, size_t out_len, size_t out_stride,
                                      int32_t* d_iterations, cudaStream_t stream) = 0;
+    // The same with an explicit workspace lane (0 or 1): two calls on different lanes and streams may be in flight
+    // at once (the BER engine keeps two batches resident); decode_batch_device is lane 0.
+    virtual bool decode_batch_device_lane(int lane, const void* d_llrs, bool is_f64, size_t llrs_len, size_t nframes,
+                                          uint32_t max_iterations, uint8_t* d_out, size_t out_len, size_t out_stride,
+                                          int32_t* d_iterations, cudaStream_t stream) = 0;
     virtual int n() const = 0;
     virtual int k() const = 0;
     virtual int edges() const = 0;

@@ -66,7 +66,11 @@ def test_north_star_bench_kernel_shape_16k_frames(oracle, monkeypatch):
 FLOAT_AT_SCALE = [
     ("ar4ja:1/2:1024", "Tanhf32", 1.6, 50, 8192, 1),
     ("ar4ja:1/2:1024", "Tanhf64", 1.6, 50, 8192, 0),
-    ("ar4ja:1/2:1024", "Phif32", 1.6, 50, 8192, 1),
+    # f32 phi(x) = -ln(tanh(x/2)) is ill-conditioned where tanh rounds towards 1 (one ulp of tanhf moves phi by up to
+    # 6 %), so libdevice-vs-glibc differences flip frames that are about to fail: 3 of 8192 at FER 3e-3; the same
+    # rule at an operating point without marginal frames must agree on every word
+    ("ar4ja:1/2:1024", "Phif32", 1.6, 50, 8192, 4),
+    ("ar4ja:1/2:1024", "Phif32", 2.6, 50, 8192, 0),
     ("ar4ja:1/2:1024", "Minstarapproxf64", 1.6, 50, 8192, 0),
     ("ar4ja:1/2:1024", "Aminstarf64", 1.6, 50, 8192, 0),
     ("nr5g:2:96", "HLTanhf32", 1.0, 30, 8192, 1),
