@@ -92,6 +92,28 @@ def test_sharding_invariance_and_determinism():
     assert a[2] > 0 and a[2] < 1000
 
 
+def test_submit_wait_two_lanes():
+    """Asynchronous form (ber.cu lanes): two batches in flight, waited in either order, add up to what the blocking
+    call gives for the same global frames; a third submit without a wait is refused."""
+    alist = codes.alist_for("dvbs2:R1_2short")
+    eng = BerEngine(alist, "Minstarapproxi8")
+    ref = eng.run(1.0, 20, 0, 1500)
+    t0 = eng.submit(1.0, 20, 0, 700)
+    t1 = eng.submit(1.0, 20, 700, 800)
+    with pytest.raises(RuntimeError):
+        eng.submit(1.0, 20, 1500, 10)
+    c = eng.wait(t1)
+    eng.wait(t0, c)
+    assert (c == ref).all()
+    with pytest.raises(RuntimeError):
+        eng.wait(t0)
+    # the pipelined driver (two rounds in flight) counts whole rounds and reproduces the blocking totals
+    t = BerTest([eng], eng.k, [1.0], max_iterations=20, max_frame_errors=10**9, batch=500, max_frames=1500)
+    assert t.pipeline_depth == 2 and t.overshoot_bound() == 500
+    st = t.run()[0]
+    assert (st.num_frames, st.ldpc.bit_errors, st.ldpc.frame_errors, st.total_iterations) == (int(ref[0]), int(ref[1]), int(ref[2]), int(ref[4]))
+
+
 def test_ber_statistical_parity_with_checker(oracle):
     """FER of the GPU engine vs the CPU checker's BER loop on the same code/decoder/Eb/N0: each inside
     the other's 3-sigma binomial band (the reference's RNG is OS-seeded, so only statistics compare)."""
