@@ -73,6 +73,12 @@ FLOAT_AT_SCALE = [
     ("ar4ja:1/2:1024", "Phif32", 2.6, 50, 8192, 0),
     ("ar4ja:1/2:1024", "Minstarapproxf64", 1.6, 50, 8192, 0),
     ("ar4ja:1/2:1024", "Aminstarf64", 1.6, 50, 8192, 0),
+    # f32 min* rules: ln(1 + e^-t) is a fast polynomial on the GPU (rules.cuh softplus_neg), gated by these
+    ("ar4ja:1/2:1024", "Minstarapproxf32", 1.6, 50, 8192, 1),
+    ("ar4ja:1/2:1024", "Aminstarf32", 1.6, 50, 8192, 1),
+    ("nr5g:2:384", "HLMinstarapproxf32", 0.25, 50, 8192, 1),        # BASELINE configs[1]
+    ("nr5g:1:384", "Aminstarf32", 0.75, 50, 4096, 1),               # BASELINE configs[3], flooding
+    ("nr5g:1:384", "HLAminstarf32", 0.75, 50, 4096, 1),             # BASELINE configs[3], layered
     ("nr5g:2:96", "HLTanhf32", 1.0, 30, 8192, 1),
     ("nr5g:2:96", "HLPhif64", 1.0, 30, 8192, 0),
 ]
