@@ -204,7 +204,7 @@ def parity_to_systematic(alist_text: str) -> str:
     a = np.zeros((nrows, words), dtype=np.uint64)
     for c, rows in enumerate(cols):
         for r in rows:
-            a[r, c >> 6] ^= np.uint64(1) << np.uint64(c & 63)
+            a[r, c >> 6] |= np.uint64(1) << np.uint64(c & 63)       # insert(): a repeated entry stays a single one (sparse.rs:114-119)
     pivots, krow = [], 0
     for j in range(ncols):                               # linalg.rs:68-104 (row echelon form over GF(2))
         if krow >= nrows:
