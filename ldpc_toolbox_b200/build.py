@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import hashlib
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -20,7 +21,7 @@ STATIC_LIB = os.path.join(OUT_DIR, "libldpc_toolbox.a")     # the reference buil
 
 # heavy kernels first: one nvcc per translation unit runs in parallel (see build())
 CU_SOURCES = ["flood_float_f64.cu", "flood_float_f32.cu", "layered_smem_f64.cu", "layered_smem_f32.cu", "layered_tile_f64.cu",
-              "layered_tile_f32.cu", "flood_i8.cu", "layered_tile_i8.cu", "layered_smem_i8.cu", "ber.cu", "capi.cu", "decoder.cu",
+              "layered_tile_f32.cu", "flood_i8.cu", "flood_i8_w16.cu", "flood_i8_w32.cu", "layered_tile_i8.cu", "layered_smem_i8.cu", "ber.cu", "capi.cu", "decoder.cu",
               "generic_bp.cu", "ingest.cu", "layered_smem.cu"]
 CPP_SOURCES = ["host.cpp"]
 
@@ -78,7 +79,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     def compile_one(src):
         # per translation unit: recompiled only when its own source, a header or the flags changed
         obj = os.path.join(OUT_DIR, src.rsplit(".", 1)[0] + ".o")
-        tu = hashlib.sha256(open(os.path.join(CSRC, src), "rb").read() + header_digest.encode()).hexdigest()
+        body = open(os.path.join(CSRC, src), "rb").read()
+        for inc in re.findall(rb'#include "([^"]+\.cu)"', body):            # a unit that includes another .cu depends on it
+            body += open(os.path.join(CSRC, inc.decode()), "rb").read()
+        tu = hashlib.sha256(body + header_digest.encode()).hexdigest()
         tu_stamp = obj + ".stamp"
         if not force and os.path.exists(obj) and os.path.exists(tu_stamp) and open(tu_stamp).read() == tu:
             return obj, f"# {src}: up to date\n", 0

@@ -625,6 +625,10 @@ private:
             fl.raw0 = ws.hard.p; fl.final_hard = ws.final_hard.p; fl.iters = ws.iters_tile.p; fl.max_iter = max_iter;
             fl.row_meta = d_row_meta_.p; fl.fused_row = d_fused_row_.p; fl.cbit = ws.cbit.p; fl.chunk_rows = chunk_rows_; fl.fuse_var_off = fuse_var_off_;
             fl.aminstar = impl_.rule == Rule::Aminstar; fl.jones = impl_.jones; fl.hardlimit = impl_.hardlimit; fl.deg1clip = impl_.deg1clip;
+            // rows beyond the register path (8 edges; 10 on 128-frame tiles) are folded from a wide shared-memory stage
+            const int reg_cap = nw == 4 ? 8 : 10;
+            fl.wide_cap = g_.max_row_deg <= reg_cap ? 0 : (g_.max_row_deg <= 16 ? 16 : 32);
+            if (const char* e = getenv("LDPC_B200_WIDE")) fl.wide_cap = atoi(e);
             fl.cluster = 1;
             while (fl.cluster < 16 && tiles * fl.cluster * 2 <= 2 * sm_count_) fl.cluster *= 2;     // up to ~2 CTAs per SM
             if (const char* e = getenv("LDPC_B200_CLUSTER")) fl.cluster = atoi(e);

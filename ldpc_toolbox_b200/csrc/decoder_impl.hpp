@@ -94,6 +94,7 @@ struct FloodI8Launch {
     int max_iter;
     bool aminstar, jones, hardlimit, deg1clip;
     int cluster;             // CTAs per tile (thread-block cluster of 1 .. 16): small batches fill the GPU this way
+    int wide_cap;            // 0: every row fits the register path; 16 / 32: kernel with one 16- / 32-line stage per warp
 };
 bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream);
 int flood_i8_max_row_degree();

@@ -345,6 +345,89 @@ __device__ __noinline__ void check_generic(uint32_t* __restrict__ msg, size_t e0
     }
 }
 
+// Rows of degree MAXD < d <= the stage capacity of the wide kernels (DVB-S2 rates >= 3/5: row degrees 10 ... 30).
+// The row's message lines stay in the warp's shared-memory stage: a word (4 frames) at a time, the four frames
+// fold side by side (four independent chains hide the IMAD -> LDS -> VIADDMNMX latency), operands are read from
+// the stage and every output word is written back in place as soon as its chain is done — input j is not needed
+// any more then (later chains start from the prefix P_{j+1}, which already contains it).  Same order as
+// check_word: for every excluded j the others are folded left to right, sharing only the prefix (arithmetic.rs:722-751).
+template <int NW, bool AMIN, bool HLIM>
+__device__ __noinline__ void check_wide(uint32_t* __restrict__ sx, int d, int lane, uint32_t skip, const Tables& tb, const Consts& k) {
+    constexpr int L = kLanes * NW;                       // words between consecutive lines of the stage
+    for (int q = 0; q < NW; ++q) {
+        if (((skip >> (4 * q)) & 0xfu) == 0xfu) continue;
+        uint32_t* w = sx + lane * NW + q;                // this lane's word of line j is w[j * L]
+        uint32_t S = 0;
+        for (int j = 0; j < d; ++j) S ^= w[j * L];
+        if (AMIN) {
+            // first minimum per frame, then the O(d) fold of the others (arithmetic.rs:1130-1192)
+            int amin[4], arg[4], delta[4], d2[4];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) { amin[f] = 1 << 20; arg[f] = 0; delta[f] = -1; }
+            for (int j = 0; j < d; ++j) {
+                const uint32_t A = abs4(w[j * L]);
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const int a = byte_of(A, f);
+                    if (a < amin[f]) { amin[f] = a; arg[f] = j; }
+                }
+            }
+            for (int j = 0; j < d; ++j) {
+                const uint32_t A = abs4(w[j * L]);
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    if (j == arg[f]) continue;
+                    const int a = byte_of(A, f);
+                    delta[f] = delta[f] < 0 ? a : hop(a, delta[f], tb, k);
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                d2[f] = hop(delta[f], amin[f], tb, k);
+                if (HLIM) { delta[f] = hardlimit(delta[f]); d2[f] = hardlimit(d2[f]); }
+            }
+            for (int j = 0; j < d; ++j) {
+                uint32_t om = 0;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) om |= (uint32_t)(j == arg[f] ? delta[f] : d2[f]) << (8 * f);
+                const uint32_t xw = w[j * L];
+                w[j * L] = apply_signs(om, sign_excluding_rt(S, xw, d), k);
+            }
+        } else {
+            int P[4] = {0, 0, 0, 0};
+            for (int j = 0; j < d; ++j) {
+                int acc[4];
+                int i = j + 1;
+                if (j == 0) {                             // the chain of output 0 starts from input 1
+                    const uint32_t A = abs4(w[L]);
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) acc[f] = byte_of(A, f);
+                    i = 2;
+                } else {
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) acc[f] = P[f];
+                }
+                for (; i < d; ++i) {
+                    const uint32_t A = abs4(w[i * L]);
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) acc[f] = gop(byte_of(A, f), acc[f], tb, k);
+                }
+                const uint32_t xw = w[j * L];
+                const uint32_t Aj = abs4(xw);
+                uint32_t om = 0;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const int mg = HLIM ? hardlimit(acc[f]) : acc[f];
+                    om |= (uint32_t)mg << (8 * f);
+                    const int aj = byte_of(Aj, f);
+                    P[f] = j == 0 ? aj : gop(aj, P[f], tb, k);
+                }
+                w[j * L] = apply_signs(om, sign_excluding_rt(S, xw, d), k);
+            }
+        }
+    }
+}
+
 // ---- variable node, arithmetic.rs:622-654, on 2 x (2 frames as s16x2) per word -----------------
 // Offset-binary bytes (value + 128) widen to unsigned 16-bit halves, so plain 32-bit adds never carry
 // between the two halves; the bias is removed inside the DPX add-min op.
@@ -553,19 +636,25 @@ __device__ __noinline__ void var_generic_class(uint32_t* __restrict__ msg, typen
     }
 }
 
-template <int NW, bool AMIN, bool HLIM>
+// WCAP = 0: the narrow kernel — two stages per warp (the next check streams in while the current one is computed),
+// a stage holds a check of up to MAXD edges.  WCAP = 16 / 32: the wide kernels for codes with rows of up to WCAP
+// edges — ONE stage of WCAP lines per warp (a wide row is ~10^4 instructions of folding per lane, the exposed load
+// latency is a few per cent), rows above MAXD are folded from shared memory by check_wide.
+template <int NW, bool AMIN, bool HLIM, int WCAP>
 __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS : 1) flood_i8_kernel(FloodI8Params p) {
     using HB = typename HBitsT<NW>::type;
     constexpr int MAXD = NW == 1 ? 10 : 8;          // check degrees with an unrolled register path
+    constexpr int SCAP = WCAP ? WCAP : MAXD;        // lines a stage can hold
+    constexpr int kStages = WCAP ? 1 : 2;
     constexpr uint32_t kAll = NW == 1 ? 0xfu : 0xffffu;
     constexpr int kFrames = kTileFrames * NW;
-    constexpr int kMsgBytes = MAXD * kLanes * NW * 4;                 // one check's message lines
+    constexpr int kMsgBytes = SCAP * kLanes * NW * 4;                 // one check's message lines
     // every region of a stage starts on a 128-byte shared-memory row: a 512-byte line read with LDS.128 (and written by
     // the TMA) then costs 4 wavefronts, not 8 — a stage size of 5184 bytes (64-byte aligned) cost 12 % of the kernel
-    constexpr int kInqOff = align128(kMsgBytes + MAXD * kLanes * (int)sizeof(HB));   // channel LLRs of the variable fused with the previous row
+    constexpr int kInqOff = align128(kMsgBytes + SCAP * kLanes * (int)sizeof(HB));   // channel LLRs of the variable fused with the previous row
     constexpr int kCbitOff = align128(kInqOff + kLanes * NW * 4);                    // previous hard decisions of the variable fused with the next row
 #ifdef LDPC_I8_SMALL_STAGE      // experiment: the round-1 stage size (valid with LDPC_B200_FUSE=0 only)
-    constexpr int kStageBytes = align128(kMsgBytes + MAXD * kLanes * (int)sizeof(HB));
+    constexpr int kStageBytes = align128(kMsgBytes + SCAP * kLanes * (int)sizeof(HB));
 #else
     constexpr int kStageBytes = align128(kCbitOff + kLanes * (int)sizeof(HB));
 #endif
@@ -666,7 +755,7 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
             // kFuseChunkRows consecutive rows (staircase fusion, decoder_impl.hpp): a stage also receives the
             // channel-LLR line of the variable fused with the previous row and the previous-iteration hard
             // decisions of the variable fused with the next row.
-            uint8_t* wbuf = dsm + (size_t)cta_warp * 2 * kStageBytes;
+            uint8_t* wbuf = dsm + (size_t)cta_warp * kStages * kStageBytes;
             const HB* cold = cbit + (size_t)((it - 1) & 1) * g.m * kLanes;      // hard decisions of iteration it-1
             HB* cnew = cbit + (size_t)(it & 1) * g.m * kLanes;                  // ... of iteration it
             const int chunk = p.chunk_rows;
@@ -676,7 +765,7 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
             auto meta_of = [&](int r) { return __ldg(reinterpret_cast<const int2*>(p.row_meta) + 2 * (size_t)min(r, g.m - 1)); };
             auto issue = [&](int stage, int r, const int2& mt) {
                 const int d = mt.y & 0xffff;
-                if (d <= MAXD && d > 0 && lane == 0) {
+                if (d <= SCAP && d > 0 && lane == 0) {
                     const bool fp = (mt.y >> 16) & 1, fn = (mt.y >> 17) & 1;
                     uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
                     const uint32_t mb = last ? 0u : (uint32_t)d * kLanes * NW * 4;
@@ -699,7 +788,7 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
             }
             // this warp's message to the variable fused with the next row: registers, or (LDPC_I8_CARRY_SMEM) a per-warp
             // shared-memory slot, which frees four registers across the fold of the next row
-            Lane<NW>* const cslot = reinterpret_cast<Lane<NW>*>(dsm + (size_t)kGroups * kWarps * 2 * kStageBytes) + (size_t)cta_warp * kLanes;
+            Lane<NW>* const cslot = reinterpret_cast<Lane<NW>*>(dsm + (size_t)kGroups * kWarps * kStages * kStageBytes) + (size_t)cta_warp * kLanes;
 #ifdef LDPC_I8_CARRY_SMEM
             Lane<NW> carry_dummy;
 #define carry carry_dummy
@@ -709,7 +798,7 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
             for (int q = 0; q < NW; ++q) carry.w[q] = 0;
 #endif
             uint32_t cold_prev = 0;          // previous-iteration hard decisions of the variable fused with the previous row
-            for (; r < g.m; stage ^= 1) {
+            for (; r < g.m; stage ^= (kStages - 1)) {
                 const int2 mt = mc;
                 const int e0 = mt.x, d = mt.y & 0xffff;
 #ifdef LDPC_I8_NOFUSE_STATIC       // experiment: compile the fusion out (valid with LDPC_B200_FUSE=0 only)
@@ -719,19 +808,27 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
 #endif
                 const int rn = next_row(r);
                 mc = mn;
-                if (rn < g.m) {
+                if (kStages == 2 && rn < g.m) {        // two stages: the next check streams in during this one
                     issue(stage ^ 1, rn, mc);
                     mn = meta_of(next_row(rn));
                 }
-                if (d <= MAXD && d > 0) {
+                if (d <= SCAP && d > 0) {
                     mbar_wait(&s_bar[cta_warp][stage], (bar_phase >> stage) & 1u);
                     bar_phase ^= 1u << stage;
                 }
-                const uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
+                uint8_t* sb = wbuf + (size_t)stage * kStageBytes;
                 uint32_t hb = 0;
-                if (d > MAXD) {
+                if (d > SCAP) {
                     for (int j = 0; j < d; ++j) hb ^= __ldcg(hbit + (size_t)(e0 + j) * kLanes + lane);
                     if (!last) check_generic<NW, AMIN, HLIM>(msg, (size_t)e0, d, lane, skip, tb, kc);
+                } else if (d > MAXD) {                 // wide row: folded in the stage, then written back line by line
+                    const HB* sh = reinterpret_cast<const HB*>(sb + kMsgBytes);
+                    for (int j = 0; j < d; ++j) hb ^= sh[j * kLanes + lane];
+                    if (!last) {
+                        check_wide<NW, AMIN, HLIM>(reinterpret_cast<uint32_t*>(sb), d, lane, skip, tb, kc);
+                        const Lane<NW>* sx = reinterpret_cast<const Lane<NW>*>(sb);
+                        for (int j = 0; j < d; ++j) st_lane<NW>(msg, (size_t)(e0 + j), lane, sx[j * kLanes + lane]);
+                    }
                 } else if (d > 0) {
                     const HB* sh = reinterpret_cast<const HB*>(sb + kMsgBytes);
 #pragma unroll
@@ -763,6 +860,10 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
                 }
                 synd |= hb;
                 __syncwarp();          // every lane is done with this stage before it is refilled
+                if (kStages == 1 && rn < g.m) {        // one stage: refill it now
+                    issue(0, rn, mc);
+                    mn = meta_of(next_row(rn));
+                }
                 r = rn;
             }
 #ifdef LDPC_I8_CARRY_SMEM
@@ -862,20 +963,21 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
     if (C > 1) cluster.sync();          // no CTA may leave while a peer can still read its shared memory
 }
 
-template <int NW, bool AMIN, bool HLIM>
+template <int NW, bool AMIN, bool HLIM, int WCAP>
 void launch_one(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t stream) {
     constexpr int MAXD = NW == 1 ? 10 : 8;
+    constexpr int SCAP = WCAP ? WCAP : MAXD, kStages = WCAP ? 1 : 2;
     constexpr int hb = (int)sizeof(typename HBitsT<NW>::type);
 #ifdef LDPC_I8_SMALL_STAGE
-    constexpr size_t stage = (size_t)align128(MAXD * kLanes * NW * 4 + MAXD * kLanes * hb);
+    constexpr size_t stage = (size_t)align128(SCAP * kLanes * NW * 4 + SCAP * kLanes * hb);
 #else
-    constexpr size_t stage = (size_t)align128(align128(align128(MAXD * kLanes * NW * 4 + MAXD * kLanes * hb) + kLanes * NW * 4) + kLanes * hb);
+    constexpr size_t stage = (size_t)align128(align128(align128(SCAP * kLanes * NW * 4 + SCAP * kLanes * hb) + kLanes * NW * 4) + kLanes * hb);
 #endif
-    constexpr size_t smem = (size_t)kGroups * kWarps * (2 * stage + (size_t)kLanes * NW * 4);     // + per-warp carry slot
+    constexpr size_t smem = (size_t)kGroups * kWarps * (kStages * stage + (size_t)kLanes * NW * 4);     // + per-warp carry slot
     // per device and cheap: set on every launch (one process may drive several GPUs)
-    cudaFuncSetAttribute(flood_i8_kernel<NW, AMIN, HLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flood_i8_kernel<NW, AMIN, HLIM, WCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int C = (kGroups == 1 && L.cluster >= 1 && L.cluster <= 16) ? L.cluster : 1;
-    if (C > 8) cudaFuncSetAttribute(flood_i8_kernel<NW, AMIN, HLIM>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (C > 8) cudaFuncSetAttribute(flood_i8_kernel<NW, AMIN, HLIM, WCAP>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(kCtaThreads);
     cfg.dynamicSmemBytes = smem;
@@ -889,45 +991,73 @@ void launch_one(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t str
         cfg.gridDim = dim3((unsigned)((L.num_tiles + kGroups - 1) / kGroups) * (unsigned)C);
         attr[0].val.clusterDim.x = (unsigned)C;
         int fit = 0;
-        if (C == 1 || (cudaOccupancyMaxActiveClusters(&fit, flood_i8_kernel<NW, AMIN, HLIM>, &cfg) == cudaSuccess && fit > 0)) break;
+        if (C == 1 || (cudaOccupancyMaxActiveClusters(&fit, flood_i8_kernel<NW, AMIN, HLIM, WCAP>, &cfg) == cudaSuccess && fit > 0)) break;
         cudaGetLastError();
     }
-    cudaLaunchKernelEx(&cfg, flood_i8_kernel<NW, AMIN, HLIM>, p);
+    cudaLaunchKernelEx(&cfg, flood_i8_kernel<NW, AMIN, HLIM, WCAP>, p);
 }
 
-template <int NW>
+template <int NW, int WCAP>
 void launch_nw(const FloodI8Launch& L, const FloodI8Params& p, cudaStream_t stream) {
 #ifdef LDPC_I8_BENCH_ONLY      // experiment builds (tools/build_variant.py): only the north-star instantiation
-    if (NW == 4 && !L.aminstar && !L.hardlimit) launch_one<4, false, false>(L, p, stream);
+    if (NW == 4 && !L.aminstar && !L.hardlimit) launch_one<4, false, false, WCAP>(L, p, stream);
 #else
     if (L.aminstar) {
-        if (L.hardlimit) launch_one<NW, true, true>(L, p, stream);
-        else launch_one<NW, true, false>(L, p, stream);
+        if (L.hardlimit) launch_one<NW, true, true, WCAP>(L, p, stream);
+        else launch_one<NW, true, false, WCAP>(L, p, stream);
     } else {
-        if (L.hardlimit) launch_one<NW, false, true>(L, p, stream);
-        else launch_one<NW, false, false>(L, p, stream);
+        if (L.hardlimit) launch_one<NW, false, true, WCAP>(L, p, stream);
+        else launch_one<NW, false, false, WCAP>(L, p, stream);
     }
 #endif
 }
 
 }  // namespace
 
-bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream) {
+// one translation unit per stage capacity (flood_i8.cu: narrow, flood_i8_w16.cu, flood_i8_w32.cu): they build in parallel
+#ifndef LDPC_I8_WCAP
+#define LDPC_I8_WCAP 0
+#endif
+#if LDPC_I8_WCAP == 16
+#define LDPC_I8_ENTRY launch_flood_i8_w16
+#elif LDPC_I8_WCAP == 32
+#define LDPC_I8_ENTRY launch_flood_i8_w32
+#else
+#define LDPC_I8_ENTRY launch_flood_i8_narrow
+#endif
+
+bool LDPC_I8_ENTRY(const FloodI8Launch& L, cudaStream_t stream) {
     FloodI8Params p;
     p.g = L.graph; p.vc = L.classes;
     p.msg = L.msg; p.hbit = L.hbit; p.inq = L.inq; p.raw0 = L.raw0; p.final_hard = L.final_hard; p.iters = L.iters;
     p.row_meta = L.row_meta; p.fused_row = L.fused_row; p.cbit = L.cbit; p.chunk_rows = L.chunk_rows; p.fuse_var_off = L.fuse_var_off;
     p.max_iter = L.max_iter; p.num_tiles = L.num_tiles; p.jones = L.jones; p.deg1clip = L.deg1clip;
     p.c_m1 = -1; p.c_one = 1; p.c_m2 = -2; p.c_ff = 0xff; p.c_sh8 = 1 << 8; p.c_sh16 = 1 << 16; p.c_sh24 = 1 << 24;
-    if (L.words_per_lane == 4) launch_nw<4>(L, p, stream);
-    else launch_nw<1>(L, p, stream);
+    if (L.words_per_lane == 4) launch_nw<4, LDPC_I8_WCAP>(L, p, stream);
+    else launch_nw<1, LDPC_I8_WCAP>(L, p, stream);
     LDPC_CUDA_CHECK(cudaGetLastError());
     return true;
 }
 
-int flood_i8_max_row_degree() { return kMaxGenericD; }
+#if LDPC_I8_WCAP == 0
+bool launch_flood_i8_w16(const FloodI8Launch& L, cudaStream_t stream);
+bool launch_flood_i8_w32(const FloodI8Launch& L, cudaStream_t stream);
 
-#ifdef LDPC_I8_PROFILE
+// stage capacity by the widest row the register path cannot take
+bool launch_flood_i8(const FloodI8Launch& L, cudaStream_t stream) {
+#ifdef LDPC_I8_BENCH_ONLY
+    return launch_flood_i8_narrow(L, stream);
+#else
+    if (L.wide_cap >= 32) return launch_flood_i8_w32(L, stream);
+    if (L.wide_cap >= 16) return launch_flood_i8_w16(L, stream);
+    return launch_flood_i8_narrow(L, stream);
+#endif
+}
+
+int flood_i8_max_row_degree() { return kMaxGenericD; }
+#endif
+
+#if defined(LDPC_I8_PROFILE) && LDPC_I8_WCAP == 0
 // experiment-only (not in include/ldpc_toolbox.h): read and reset the per-pass cycle counters
 extern "C" void ldpc_toolbox_debug_i8_profile(unsigned long long* out) {
     cudaDeviceSynchronize();
