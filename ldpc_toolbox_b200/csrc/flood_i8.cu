@@ -354,12 +354,12 @@ __device__ __noinline__ void check_generic(uint32_t* __restrict__ msg, size_t e0
 template <int NW, bool AMIN, bool HLIM>
 __device__ __noinline__ void check_wide(uint32_t* __restrict__ sx, int d, int lane, uint32_t skip, const Tables& tb, const Consts& k) {
     constexpr int L = kLanes * NW;                       // words between consecutive lines of the stage
-    for (int q = 0; q < NW; ++q) {
-        if (((skip >> (4 * q)) & 0xfu) == 0xfu) continue;
-        uint32_t* w = sx + lane * NW + q;                // this lane's word of line j is w[j * L]
-        uint32_t S = 0;
-        for (int j = 0; j < d; ++j) S ^= w[j * L];
-        if (AMIN) {
+    if (AMIN) {
+        for (int q = 0; q < NW; ++q) {
+            if (((skip >> (4 * q)) & 0xfu) == 0xfu) continue;
+            uint32_t* w = sx + lane * NW + q;            // this lane's word of line j is w[j * L]
+            uint32_t S = 0;
+            for (int j = 0; j < d; ++j) S ^= w[j * L];
             // first minimum per frame, then the O(d) fold of the others (arithmetic.rs:1130-1192)
             int amin[4], arg[4], delta[4], d2[4];
 #pragma unroll
@@ -393,36 +393,67 @@ __device__ __noinline__ void check_wide(uint32_t* __restrict__ sx, int d, int la
                 const uint32_t xw = w[j * L];
                 w[j * L] = apply_signs(om, sign_excluding_rt(S, xw, d), k);
             }
-        } else {
-            int P[4] = {0, 0, 0, 0};
+        }
+    } else {
+        // W words (4 W frames) fold side by side: 8 independent chains on 512-frame tiles
+        constexpr int W = NW >= 2 ? 2 : 1;
+        for (int q = 0; q < NW; q += W) {
+            if (((skip >> (4 * q)) & ((1u << (4 * W)) - 1u)) == ((1u << (4 * W)) - 1u)) continue;
+            uint32_t* w = sx + lane * NW + q;            // word u of this lane in line j is w[j * L + u]
+            uint32_t S[W];
+#pragma unroll
+            for (int u = 0; u < W; ++u) S[u] = 0;
+            for (int j = 0; j < d; ++j)
+#pragma unroll
+                for (int u = 0; u < W; ++u) S[u] ^= w[j * L + u];
+            int P[W][4];
             for (int j = 0; j < d; ++j) {
-                int acc[4];
+                int acc[W][4];
                 int i = j + 1;
                 if (j == 0) {                             // the chain of output 0 starts from input 1
-                    const uint32_t A = abs4(w[L]);
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) acc[f] = byte_of(A, f);
+                    for (int u = 0; u < W; ++u) {
+                        const uint32_t A = abs4(w[L + u]);
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) acc[u][f] = byte_of(A, f);
+                    }
                     i = 2;
                 } else {
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) acc[f] = P[f];
+                    for (int u = 0; u < W; ++u)
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) acc[u][f] = P[u][f];
                 }
+                uint32_t nxt[W];                          // operands of the next step are in flight during this one
+#pragma unroll
+                for (int u = 0; u < W; ++u) nxt[u] = i < d ? w[i * L + u] : 0u;
                 for (; i < d; ++i) {
-                    const uint32_t A = abs4(w[i * L]);
+                    uint32_t A[W];
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) acc[f] = gop(byte_of(A, f), acc[f], tb, k);
-                }
-                const uint32_t xw = w[j * L];
-                const uint32_t Aj = abs4(xw);
-                uint32_t om = 0;
+                    for (int u = 0; u < W; ++u) A[u] = abs4(nxt[u]);
+                    if (i + 1 < d) {
 #pragma unroll
-                for (int f = 0; f < 4; ++f) {
-                    const int mg = HLIM ? hardlimit(acc[f]) : acc[f];
-                    om |= (uint32_t)mg << (8 * f);
-                    const int aj = byte_of(Aj, f);
-                    P[f] = j == 0 ? aj : gop(aj, P[f], tb, k);
+                        for (int u = 0; u < W; ++u) nxt[u] = w[(i + 1) * L + u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < W; ++u)
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) acc[u][f] = gop(byte_of(A[u], f), acc[u][f], tb, k);
                 }
-                w[j * L] = apply_signs(om, sign_excluding_rt(S, xw, d), k);
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    const uint32_t xw = w[j * L + u];
+                    const uint32_t Aj = abs4(xw);
+                    uint32_t om = 0;
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        const int mg = HLIM ? hardlimit(acc[u][f]) : acc[u][f];
+                        om |= (uint32_t)mg << (8 * f);
+                        const int aj = byte_of(Aj, f);
+                        P[u][f] = j == 0 ? aj : gop(aj, P[u][f], tb, k);
+                    }
+                    w[j * L + u] = apply_signs(om, sign_excluding_rt(S[u], xw, d), k);
+                }
             }
         }
     }
