@@ -79,7 +79,8 @@ struct FloodI8Launch {
     DeviceGraph graph;
     VarClasses classes;
     const RowMeta* row_meta; // m records
-    const int* fused_row;    // n entries: row r whose last slot holds the variable when it is fused, else -1
+    const int* snap_src;     // n entries: >= 0 first row-major edge of the variable, <= -2 fused (row -2 - x), -1 no checks
+    int snap_n;              // variables whose final hard decisions are read back (output_len)
     void* cbit;              // [tiles][2][m][32] hard decisions of the fused variables, by iteration parity (u8 / u16 per lane)
     int chunk_rows;          // rows per chunk (power of two), the same value the row records were built with
     int fuse_var_off;        // every fused variable satisfies v = (row of its second check) + fuse_var_off

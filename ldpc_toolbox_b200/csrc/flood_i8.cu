@@ -59,7 +59,8 @@ struct FloodI8Params {
     const void* raw0;       // [tiles][n][32]     raw-sign hard decisions (x <= 0.0), 4*NW bits per lane
     void* final_hard;       // [tiles][n][32]     snapshot taken when a frame stops
     const RowMeta* row_meta;  // [m]              per-row record: first edge, degree, staircase-fusion flags (decoder_impl.hpp)
-    const int* fused_row;     // [n]              row whose last slot holds the variable when it is fused, else -1
+    const int* snap_src;      // [n]              where a variable's hard decisions live (see the stop logic)
+    int snap_n;               //                  variables whose final decisions are read back (the caller's output_len)
     void* cbit;             // [tiles][2][m][32]  hard decisions of the fused variables by iteration parity, 4*NW bits per lane
     int chunk_rows;         // rows per chunk dealt to a warp in the check pass (power of two)
     int fuse_var_off;       // the variable fused between rows r-1 and r is r + fuse_var_off (staircase: k - 1)
@@ -917,23 +918,38 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
         if (warp == 0) s_unsat_g[grp][(it & 1) ^ 1][lane] = 0;     // next iteration's words; their last readers are past the barrier above
         if (any) {
             if (stop) {
-                for (int v = gw; v < g.n; v += nw) {
-                    size_t o = (size_t)v * kLanes + lane;
-                    int p0 = __ldg(g.col_ptr + v), p1 = __ldg(g.col_ptr + v + 1);
-                    uint32_t hb;
-                    const int fr = __ldg(p.fused_row + v);
-                    if (fr >= 0) hb = __ldcg(cbit + ((size_t)((it - 1) & 1) * g.m + fr) * kLanes + lane);      // fused variable: decisions of iteration it-1
-                    else if (p1 > p0) hb = __ldcg(hbit + (size_t)__ldg(g.col_edge + p0) * kLanes + lane);
-                    else if (it == 1) hb = raw0[o];
-                    else {                            // isolated variable: posterior = quantised input
-                        hb = 0;
-                        for (int q = 0; q < NW; ++q) {
-                            uint32_t qw = __ldg(inq + o * NW + q);
+                // Only the first snap_n variables are ever read back (the caller's output_len).  snap_src[v] names the
+                // line holding v's hard decisions of iteration it-1: >= 0 the hbit line of its first edge, <= -2 the
+                // cbit line of row -2 - x (fused variable), -1 a variable without checks.  Four variables per step so the
+                // index -> line -> merge chains overlap (this loop runs whenever a frame stops: every iteration in
+                // the waterfall region).
+                auto snap_one = [&](int v, int src) -> uint32_t {
+                    if (src >= 0) return __ldcg(hbit + (size_t)src * kLanes + lane);
+                    if (src <= -2) return __ldcg(cbit + ((size_t)((it - 1) & 1) * g.m + (size_t)(-2 - src)) * kLanes + lane);
+                    const size_t o = (size_t)v * kLanes + lane;
+                    if (it == 1) return raw0[o];
+                    uint32_t hb = 0;                      // isolated variable: posterior = quantised input
+                    for (int q = 0; q < NW; ++q) {
+                        const uint32_t qw = __ldg(inq + o * NW + q);
 #pragma unroll
-                            for (int b = 0; b < 4; ++b) hb |= (uint32_t)(((qw >> (8 * b)) & 0xffu) <= 128u) << (4 * q + b);
-                        }
+                        for (int b = 0; b < 4; ++b) hb |= (uint32_t)(((qw >> (8 * b)) & 0xffu) <= 128u) << (4 * q + b);
                     }
-                    fin[o] = (HB)((fin[o] & ~stop) | (hb & stop));
+                    return hb;
+                };
+                for (int v0 = gw * 4; v0 < p.snap_n; v0 += nw * 4) {
+                    int src[4];
+                    uint32_t hb[4], old[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) src[u] = __ldg(p.snap_src + min(v0 + u, p.snap_n - 1));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int v = min(v0 + u, p.snap_n - 1);
+                        hb[u] = snap_one(v, src[u]);
+                        old[u] = fin[(size_t)v * kLanes + lane];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (v0 + u < p.snap_n) fin[(size_t)(v0 + u) * kLanes + lane] = (HB)((old[u] & ~stop) | (hb[u] & stop));
                 }
             }
             if (warp == 0) {
@@ -1061,7 +1077,7 @@ bool LDPC_I8_ENTRY(const FloodI8Launch& L, cudaStream_t stream) {
     FloodI8Params p;
     p.g = L.graph; p.vc = L.classes;
     p.msg = L.msg; p.hbit = L.hbit; p.inq = L.inq; p.raw0 = L.raw0; p.final_hard = L.final_hard; p.iters = L.iters;
-    p.row_meta = L.row_meta; p.fused_row = L.fused_row; p.cbit = L.cbit; p.chunk_rows = L.chunk_rows; p.fuse_var_off = L.fuse_var_off;
+    p.row_meta = L.row_meta; p.snap_src = L.snap_src; p.snap_n = L.snap_n; p.cbit = L.cbit; p.chunk_rows = L.chunk_rows; p.fuse_var_off = L.fuse_var_off;
     p.max_iter = L.max_iter; p.num_tiles = L.num_tiles; p.jones = L.jones; p.deg1clip = L.deg1clip;
     p.c_m1 = -1; p.c_one = 1; p.c_m2 = -2; p.c_ff = 0xff; p.c_sh8 = 1 << 8; p.c_sh16 = 1 << 16; p.c_sh24 = 1 << 24;
     if (L.words_per_lane == 4) launch_nw<4, LDPC_I8_WCAP>(L, p, stream);

@@ -8,6 +8,7 @@
 // emit:   final hard-decision plane -> [frame][bit] one byte per bit (DecoderOutput.codeword,
 //   reference src/decoder.rs:39-48), first out_len bits of each frame (c_api/decoder.rs:61).
 #include <string>
+#include <type_traits>
 
 #include "decoder_impl.hpp"
 #include "device_common.cuh"
@@ -76,31 +77,39 @@ __global__ void __launch_bounds__(kIngestWarps * 32) ingest_kernel(IngestLaunch 
     }
 }
 
-constexpr int kEmitChunk = 32;
+constexpr int kEmitVars = 128;     // variables per CTA: every frame row is written 128 bytes at a time
 
+// A CTA turns the decision masks of 128 variables of one tile into 128 consecutive output bytes of each of the tile's
+// frames: masks are staged transposed in shared memory ([lane][variable], so the four masks a thread needs are adjacent),
+// then a thread writes four 0/1 bytes of one frame as one 32-bit store (a warp = one full 128-byte row segment).
 template <int NW>
 __global__ void __launch_bounds__(256) emit_kernel(EmitLaunch p) {
-    constexpr int TF = kTileFrames * NW, ST = kEmitChunk + 4;
-    __shared__ uint8_t s[TF * ST];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    using HB = typename std::conditional<NW == 1, uint8_t, uint16_t>::type;
+    constexpr int TF = kTileFrames * NW, FPL = 4 * NW;              // frames per tile / per lane
+    __shared__ HB s_m[kLanes][kEmitVars + 4];
     const size_t tile = blockIdx.x;
-    const size_t v0 = (size_t)blockIdx.y * kEmitChunk;
-    for (int vv = warp; vv < kEmitChunk; vv += 8) {
-        size_t v = v0 + vv;
-        uint32_t b = 0;
-        if (v < p.out_len) {
-            size_t o = (tile * (size_t)p.n + v) * kLanes + lane;
-            b = NW == 1 ? static_cast<const uint8_t*>(p.final_hard)[o] : static_cast<const uint16_t*>(p.final_hard)[o];
-        }
-#pragma unroll
-        for (int k = 0; k < 4 * NW; ++k) s[(lane * 4 * NW + k) * ST + vv] = (b >> k) & 1;
+    const size_t v0 = (size_t)blockIdx.y * kEmitVars;
+    const HB* fin = static_cast<const HB*>(p.final_hard) + tile * (size_t)p.n * kLanes;
+    for (int idx = threadIdx.x; idx < kEmitVars * kLanes; idx += blockDim.x) {
+        const int v = idx >> 5, ln = idx & 31;
+        s_m[ln][v] = v0 + v < p.out_len ? fin[(v0 + v) * kLanes + ln] : (HB)0;
     }
     __syncthreads();
-    for (int fr = warp; fr < TF; fr += 8) {
-        size_t frame = tile * TF + fr;
+    const bool aligned = (((uintptr_t)p.out | p.out_stride | v0) & 3u) == 0;
+    for (int idx = threadIdx.x; idx < TF * (kEmitVars / 4); idx += blockDim.x) {
+        const int fr = idx >> 5, g4 = idx & 31;                       // frame of the tile, group of four variables
+        const size_t frame = tile * TF + fr;
         if (frame >= p.nframes) break;
-        size_t v = v0 + lane;
-        if (v < p.out_len) p.out[frame * p.out_stride + v] = s[fr * ST + lane];
+        const int ln = fr / FPL, bit = fr % FPL;
+        const size_t v = v0 + 4 * (size_t)g4;
+        if (v >= p.out_len) continue;
+        uint32_t w = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w |= (uint32_t)((s_m[ln][4 * g4 + i] >> bit) & 1u) << (8 * i);
+        uint8_t* dst = p.out + frame * p.out_stride + v;
+        if (aligned && v + 4 <= p.out_len) *reinterpret_cast<uint32_t*>(dst) = w;
+        else
+            for (int i = 0; i < 4 && v + i < p.out_len; ++i) dst[i] = (uint8_t)(w >> (8 * i));
     }
 }
 
@@ -148,7 +157,7 @@ bool launch_ingest(const IngestLaunch& L, cudaStream_t stream) {
 
 bool launch_emit(const EmitLaunch& L, cudaStream_t stream) {
     if (L.num_tiles == 0 || L.out_len == 0) return true;
-    dim3 grid((unsigned)L.num_tiles, (unsigned)((L.out_len + kEmitChunk - 1) / kEmitChunk)), block(256);
+    dim3 grid((unsigned)L.num_tiles, (unsigned)((L.out_len + kEmitVars - 1) / kEmitVars)), block(256);
     if (L.words_per_lane == 4) emit_kernel<4><<<grid, block, 0, stream>>>(L);
     else emit_kernel<1><<<grid, block, 0, stream>>>(L);
     LDPC_CUDA_CHECK(cudaGetLastError());
