@@ -39,7 +39,19 @@ for name in a.configs.split(","):
         frames = a.frames
     if a.points:
         points = [float(x) for x in a.points.split(",")]
-    eng = BerEngine(codes.cached_alist_path(spec), impl, punct, device=0)
+    path = codes.cached_alist_path(spec)
+    head = open(path).read().split("\n", 4)
+    n_cw = int(head[0].split()[0])
+    edges = sum(int(x) for x in head[2].split())                     # column weights
+    layered = impl.startswith("HL")
+    s_msg = 8 if impl.endswith("f64") else (4 if impl.endswith("f32") else 1)
+    # 4 E s bytes per frame-iteration (flooding), 2 E s (layered), + f32 LLRs in + packed bits out
+    bytes_per_frame_it = (2 if layered else 4) * edges * s_msg
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        peak = 6650.0
+    eng = BerEngine(path, impl, punct, device=0)
     for ebn0 in points:
         eng.run(ebn0, max_iter, 0, frames)            # warm-up (allocations, first launch)
         best, c = None, None
@@ -52,5 +64,10 @@ for name in a.configs.split(","):
         print(json.dumps({"config": name, "code": spec, "impl": impl, "max_iter": max_iter, "ebn0_db": ebn0, "frames": frames,
                           "seconds": round(best, 4), "info_gbps": round(eng.k * frames / best / 1e9, 5),
                           "frames_per_s": round(frames / best, 1), "avg_iterations": round(d["total_iterations"] / frames, 3),
-                          "fer": d["frame_errors"] / frames, "ber": d["bit_errors"] / (frames * eng.k)}), flush=True)
+                          "fer": d["frame_errors"] / frames, "ber": d["bit_errors"] / (frames * eng.k),
+                          "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame_iteration": bytes_per_frame_it,
+                                       "achieved_gbs": round((d["total_iterations"] * bytes_per_frame_it + frames * (n_cw * 4 + n_cw / 8)) / best / 1e9, 1),
+                                       "peak_gbs": peak,
+                                       "frac": round((d["total_iterations"] * bytes_per_frame_it + frames * (n_cw * 4 + n_cw / 8)) / best / 1e9 / peak, 4),
+                                       "note": "whole on-device BER pipeline (front-end + decode + back-end) in the denominator"}}), flush=True)
     eng.close()
