@@ -206,15 +206,18 @@ __global__ void __launch_bounds__(256) ber_frontend_kernel(FrontendParams p) {
     // (a bit interleaver in front of BPSK only renames i.i.d. noise samples, so it is the identity here)
     for (int t4 = threadIdx.x; t4 * 4 < p.n_tx; t4 += blockDim.x) {
         uint4 r = rng(f_lo, f_hi, (uint32_t)t4, kStreamNoise);
-        // Box-Muller on (u1, u2) pairs; u1 in (0,1] with full 32-bit resolution, log in f64
+        // Box-Muller on (u1, u2) pairs.  u1 = (x + 0.5) 2^-32 keeps the 32-bit resolution where it matters — near 0, where
+        // the float is exact and the radius reaches sqrt(-2 ln 2^-33) = 6.76 sigma; near 1 it rounds to a multiple of
+        // 2^-24 (radius steps of 3e-4 sigma around 0).  f32 logf / sqrtf (1 ulp) instead of the f64 pair of round 1:
+        // the front-end kernel was 7 % of a BER batch, most of it here.
         float z[4];
         {
-            double r0 = sqrt(-2.0 * log(((double)r.x + 0.5) * 2.3283064365386963e-10));
-            double r1 = sqrt(-2.0 * log(((double)r.z + 0.5) * 2.3283064365386963e-10));
+            const float r0 = sqrtf(-2.0f * logf(fminf(((float)r.x + 0.5f) * 2.3283064365386963e-10f, 1.0f)));
+            const float r1 = sqrtf(-2.0f * logf(fminf(((float)r.z + 0.5f) * 2.3283064365386963e-10f, 1.0f)));
             float s0, c0, s1, c1;
             sincospif(2.0f * ((float)(r.y >> 8) + 0.5f) * 5.9604644775390625e-8f, &s0, &c0);
             sincospif(2.0f * ((float)(r.w >> 8) + 0.5f) * 5.9604644775390625e-8f, &s1, &c1);
-            z[0] = (float)r0 * c0; z[1] = (float)r0 * s0; z[2] = (float)r1 * c1; z[3] = (float)r1 * s1;
+            z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
