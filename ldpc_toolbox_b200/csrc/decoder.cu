@@ -630,7 +630,7 @@ private:
             fl.graph = dg_; fl.classes = vc_; fl.num_tiles = tiles; fl.words_per_lane = nw;
             fl.msg = reinterpret_cast<uint32_t*>(ws.msg.p); fl.hbit = ws.hbit.p; fl.inq = reinterpret_cast<const uint32_t*>(ws.inq.p);
             fl.raw0 = ws.hard.p; fl.final_hard = ws.final_hard.p; fl.iters = ws.iters_tile.p; fl.max_iter = max_iter;
-            fl.row_meta = d_row_meta_.p; fl.snap_src = d_fused_row_.p; fl.snap_n = (int)std::min<size_t>(out_len, (size_t)g_.n); fl.cbit = ws.cbit.p; fl.chunk_rows = chunk_rows_; fl.fuse_var_off = fuse_var_off_;
+            fl.row_meta = d_row_meta_.p; fl.snap_src = d_fused_row_.p; fl.snap_n = (int)std::min<size_t>(out_len, (size_t)g_.n); fl.cbit = ws.cbit.p; fl.chunk_rows = chunk_rows_; fl.fuse_var_off = fuse_var_off_; fl.graph_max_row_deg = g_.max_row_deg;
             fl.aminstar = impl_.rule == Rule::Aminstar; fl.jones = impl_.jones; fl.hardlimit = impl_.hardlimit; fl.deg1clip = impl_.deg1clip;
             // rows beyond the register path (8 edges; 10 on 128-frame tiles) are folded from a wide shared-memory stage
             const int reg_cap = nw == 4 ? 8 : 10;

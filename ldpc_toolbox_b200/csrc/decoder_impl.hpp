@@ -84,6 +84,7 @@ struct FloodI8Launch {
     void* cbit;              // [tiles][2][m][32] hard decisions of the fused variables, by iteration parity (u8 / u16 per lane)
     int chunk_rows;          // rows per chunk (power of two), the same value the row records were built with
     int fuse_var_off;        // every fused variable satisfies v = (row of its second check) + fuse_var_off
+    int graph_max_row_deg;   // largest check degree (rows beyond the stage capacity keep an explicit initialisation)
     int num_tiles;
     int words_per_lane;      // 1 or 4
     uint32_t* msg;

@@ -64,6 +64,7 @@ struct FloodI8Params {
     void* cbit;             // [tiles][2][m][32]  hard decisions of the fused variables by iteration parity, 4*NW bits per lane
     int chunk_rows;         // rows per chunk dealt to a warp in the check pass (power of two)
     int fuse_var_off;       // the variable fused between rows r-1 and r is r + fuse_var_off (staircase: k - 1)
+    int max_row_deg;        // largest check degree of the code
     int32_t* iters;         // [tiles*128*NW]     iterations, or -1 on failure
     int max_iter;
     int num_tiles;
@@ -678,6 +679,14 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
     constexpr int MAXD = NW == 1 ? 10 : 8;          // check degrees with an unrolled register path
     constexpr int SCAP = WCAP ? WCAP : MAXD;        // lines a stage can hold
     constexpr int kStages = WCAP ? 1 : 2;
+#ifdef LDPC_I8_GATHER_FIRST
+    // experiment (kept, off): no initialisation pass — iteration 1 stages every row straight from the channel-LLR /
+    // raw-sign lines of its variables, one bulk copy per line.  Saves a write and a read of the message array
+    // (~16 ms of 820) but the extra code in the staging path costs the steady-state loop 7 %: 858 vs 818 ms.
+    constexpr bool kGatherFirst = true;
+#else
+    constexpr bool kGatherFirst = false;
+#endif
     constexpr uint32_t kAll = NW == 1 ? 0xfu : 0xffffu;
     constexpr int kFrames = kTileFrames * NW;
     constexpr int kMsgBytes = SCAP * kLanes * NW * 4;                 // one check's message lines
@@ -740,9 +749,10 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
     __syncthreads();
     PROF_T(pt_init0);
 
-    // flooding.rs:88-100: first variable messages are the quantised channel LLRs; the
-    // "iteration 0" hard decisions are the raw LLR signs (flooding.rs:57).  Edge-parallel, four
-    // independent edges in flight per warp.
+    // flooding.rs:88-100: the first variable messages are the quantised channel LLRs and the "iteration 0" hard
+    // decisions the raw LLR signs (flooding.rs:57).  Edge-parallel, four independent edges in flight per warp.
+    // (With LDPC_I8_GATHER_FIRST only rows too wide for a stage are initialised here.)
+#ifndef LDPC_I8_GATHER_FIRST
     for (int e0 = gw * 4; active && e0 < g.E; e0 += nw * 4) {
         int v[4];
         Lane<NW> w[4];
@@ -759,6 +769,20 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
         const int4 mt = __ldg(reinterpret_cast<const int4*>(p.row_meta) + r);
         if ((mt.y >> 17) & 1) cbit[(size_t)r * kLanes + lane] = raw0[(size_t)mt.w * kLanes + lane];
     }
+#else
+    if (p.max_row_deg > SCAP) {
+        for (int r = gw; active && r < g.m; r += nw) {
+            const int2 mt = __ldg(reinterpret_cast<const int2*>(p.row_meta) + 2 * (size_t)r);
+            const int d = mt.y & 0xffff;
+            if (d <= SCAP) continue;
+            for (int j = 0; j < d; ++j) {
+                const int v = __ldg(g.col_idx + mt.x + j);
+                st_lane<NW>(msg, (size_t)(mt.x + j), lane, ld_lane<NW>(inq, (size_t)v, lane));
+                hbit[(size_t)(mt.x + j) * kLanes + lane] = raw0[(size_t)v * kLanes + lane];
+            }
+        }
+    }
+#endif
     if (C > 1) cluster.sync();
     else __syncthreads();
     PROF_T(pt_init1);
@@ -805,10 +829,24 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
                     const uint32_t hbytes = nh * kLanes * (uint32_t)sizeof(HB);
                     const uint32_t ib = (fp && !last) ? (uint32_t)kLanes * NW * 4 : 0u, cb = fn ? (uint32_t)kLanes * (uint32_t)sizeof(HB) : 0u;
                     mbar_expect_tx(&s_bar[cta_warp][stage], mb + hbytes + ib + cb);
-                    if (mb) bulk_g2s(sb, msg + (size_t)mt.x * kLanes * NW, mb, &s_bar[cta_warp][stage]);
-                    if (hbytes) bulk_g2s(sb + kMsgBytes, hbit + (size_t)mt.x * kLanes, hbytes, &s_bar[cta_warp][stage]);
+                    if (kGatherFirst && it == 1) {
+                        // iteration 1: a row's incoming messages ARE the channel LLRs of its variables and the decisions
+                        // of "iteration 0" their raw signs — one bulk copy per variable line instead of one per row
+                        constexpr uint32_t kLine = kLanes * NW * 4, kHLine = kLanes * (uint32_t)sizeof(HB);
+                        int vlast = 0;
+                        for (int j = 0; j < d; ++j) {
+                            const int v = __ldg(g.col_idx + mt.x + j);
+                            if (mb) bulk_g2s(sb + (uint32_t)j * kLine, inq + (size_t)v * kLanes * NW, kLine, &s_bar[cta_warp][stage]);
+                            if ((uint32_t)j < nh) bulk_g2s(sb + kMsgBytes + (uint32_t)j * kHLine, raw0 + (size_t)v * kLanes, kHLine, &s_bar[cta_warp][stage]);
+                            vlast = v;
+                        }
+                        if (cb) bulk_g2s(sb + kCbitOff, raw0 + (size_t)vlast * kLanes, cb, &s_bar[cta_warp][stage]);
+                    } else {
+                        if (mb) bulk_g2s(sb, msg + (size_t)mt.x * kLanes * NW, mb, &s_bar[cta_warp][stage]);
+                        if (hbytes) bulk_g2s(sb + kMsgBytes, hbit + (size_t)mt.x * kLanes, hbytes, &s_bar[cta_warp][stage]);
+                        if (cb) bulk_g2s(sb + kCbitOff, cold + (size_t)r * kLanes, cb, &s_bar[cta_warp][stage]);
+                    }
                     if (ib) bulk_g2s(sb + kInqOff, inq + (size_t)(r + p.fuse_var_off) * kLanes * NW, ib, &s_bar[cta_warp][stage]);
-                    if (cb) bulk_g2s(sb + kCbitOff, cold + (size_t)r * kLanes, cb, &s_bar[cta_warp][stage]);
                 }
             };
             int r = gw * chunk, stage = 0;
@@ -924,6 +962,7 @@ __global__ void __launch_bounds__(kCtaThreads, kGroups == 1 ? LDPC_I8_MINBLOCKS 
                 // index -> line -> merge chains overlap (this loop runs whenever a frame stops: every iteration in
                 // the waterfall region).
                 auto snap_one = [&](int v, int src) -> uint32_t {
+                    if (kGatherFirst && it == 1) return raw0[(size_t)v * kLanes + lane];      // the per-edge lines are not written yet
                     if (src >= 0) return __ldcg(hbit + (size_t)src * kLanes + lane);
                     if (src <= -2) return __ldcg(cbit + ((size_t)((it - 1) & 1) * g.m + (size_t)(-2 - src)) * kLanes + lane);
                     const size_t o = (size_t)v * kLanes + lane;
@@ -1077,7 +1116,7 @@ bool LDPC_I8_ENTRY(const FloodI8Launch& L, cudaStream_t stream) {
     FloodI8Params p;
     p.g = L.graph; p.vc = L.classes;
     p.msg = L.msg; p.hbit = L.hbit; p.inq = L.inq; p.raw0 = L.raw0; p.final_hard = L.final_hard; p.iters = L.iters;
-    p.row_meta = L.row_meta; p.snap_src = L.snap_src; p.snap_n = L.snap_n; p.cbit = L.cbit; p.chunk_rows = L.chunk_rows; p.fuse_var_off = L.fuse_var_off;
+    p.row_meta = L.row_meta; p.snap_src = L.snap_src; p.snap_n = L.snap_n; p.cbit = L.cbit; p.chunk_rows = L.chunk_rows; p.fuse_var_off = L.fuse_var_off; p.max_row_deg = L.graph_max_row_deg;
     p.max_iter = L.max_iter; p.num_tiles = L.num_tiles; p.jones = L.jones; p.deg1clip = L.deg1clip;
     p.c_m1 = -1; p.c_one = 1; p.c_m2 = -2; p.c_ff = 0xff; p.c_sh8 = 1 << 8; p.c_sh16 = 1 << 16; p.c_sh24 = 1 << 24;
     if (L.words_per_lane == 4) launch_nw<4, LDPC_I8_WCAP>(L, p, stream);
