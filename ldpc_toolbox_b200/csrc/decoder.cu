@@ -366,9 +366,12 @@ private:
             cap = std::min(cap, fit);
         }
         const size_t need = (nframes + kTileFrames - 1) / kTileFrames;
+        // a batch that does not fit one launch is cut into EQUAL chunks (a large chunk plus a small tail would push the
+        // tail onto the 128-frame-tile kernel, which streams HBM at half the rate)
+        if (need > cap) cap = (need + (need + cap - 1) / cap - 1) / ((need + cap - 1) / cap);
         size_t frames = std::max<size_t>(1, std::min(need, cap)) * kTileFrames;
         const size_t tf = (size_t)kTileFrames * pick_nw(frames);
-        if (frames > tf) frames = frames / tf * tf;           // whole tiles per launch (the last chunk may be ragged)
+        if (frames > tf) frames = (need > cap ? (frames + tf - 1) / tf : frames / tf) * tf;   // whole tiles per launch (the last chunk may be ragged)
         else frames = tf;
         return frames;
     }
