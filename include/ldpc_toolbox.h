@@ -139,6 +139,10 @@ size_t ldpc_toolbox_decoder_llrs_len(void *decoder);       /* expected llrs_len 
 /* device time in ms of the stages of the last processed chunk: [ingest, decode, emit];
  * returns the number of kernels launched by this handle so far */
 int64_t ldpc_toolbox_decoder_last_timing(void *decoder, float *ms3);
+/* average device time in ms of the BP kernel over the launches (flooding / layered-tile kernels) since the previous
+ * call — at most the last 32 — and their number; CUDA events on the launching stream, resolved here, so a caller
+ * can time back-to-back calls without synchronising after each of them */
+float ldpc_toolbox_decoder_average_decode_ms(void *decoder, int64_t *launches);
 
 /* On-device BER Monte-Carlo engine (BPSK/AWGN), the GPU counterpart of the reference's
  * BerTest/Worker loop (reference src/simulation/ber.rs:246-282, :297-368, :436-481).

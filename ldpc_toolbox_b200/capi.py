@@ -38,6 +38,7 @@ _SIGS = {
     "ldpc_toolbox_decoder_num_edges": (C.c_size_t, [C.c_void_p]),
     "ldpc_toolbox_decoder_llrs_len": (C.c_size_t, [C.c_void_p]),
     "ldpc_toolbox_decoder_last_timing": (C.c_int64, [C.c_void_p, C.c_void_p]),
+    "ldpc_toolbox_decoder_average_decode_ms": (C.c_float, [C.c_void_p, C.c_void_p]),
     "ldpc_toolbox_ber_ctor": (C.c_void_p, [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int]),
     "ldpc_toolbox_ber_dtor": (None, [C.c_void_p]),
     "ldpc_toolbox_ber_set_modulation": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int32]),

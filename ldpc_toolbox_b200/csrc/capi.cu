@@ -12,6 +12,7 @@
 
 namespace ldpc {
 void resolve_decoder_stats(LdpcDecoder* d);
+float average_decode_ms(LdpcDecoder* d, int64_t* launches);
 }
 
 using namespace ldpc;
@@ -227,6 +228,12 @@ int64_t ldpc_toolbox_decoder_last_timing(void* d, float* ms3) {
     const BatchStats& s = dec->stats();
     if (ms3) { ms3[0] = s.ingest_ms; ms3[1] = s.decode_ms; ms3[2] = s.emit_ms; }
     return s.kernel_launches;
+}
+
+float ldpc_toolbox_decoder_average_decode_ms(void* d, int64_t* launches) {
+    if (launches) *launches = 0;
+    if (!d) return 0.0f;
+    return average_decode_ms(static_cast<DecoderHandle*>(d)->decoder.get(), launches);
 }
 
 void* ldpc_toolbox_encoder_ctor(const char* alist_file_path, const char* puncturing) {

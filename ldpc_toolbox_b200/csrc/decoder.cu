@@ -88,6 +88,7 @@ public:
         if (h2d_stream_) cudaStreamDestroy(h2d_stream_);
         if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
         for (auto& e : ev_) if (e) cudaEventDestroy(e);
+        for (auto& pr : ring_) for (auto& e : pr) if (e) cudaEventDestroy(e);
         if (ev_hist_) cudaEventDestroy(ev_hist_);
         if (h_hist_) cudaFreeHost(h_hist_);
         for (auto& sl : slot_)
@@ -151,6 +152,8 @@ public:
         }
         LDPC_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
         for (auto& e : ev_) LDPC_CUDA_CHECK(cudaEventCreate(&e));
+        for (auto& pr : ring_) { LDPC_CUDA_CHECK(cudaEventCreate(&pr[0])); LDPC_CUDA_CHECK(cudaEventCreate(&pr[1])); }
+        ring_ok_ = true;
         max_tiles_opt_ = opt.max_tiles;
         nw_opt_ = opt.words_per_lane;
         if (const char* e = getenv("LDPC_B200_NW")) nw_opt_ = atoi(e);
@@ -625,6 +628,7 @@ private:
         else in.in_i16 = reinterpret_cast<int16_t*>(ws.inq.p);
         if (!launch_ingest(in, s)) return false;
         if (ev_begin) cudaEventRecord(ev_[1], s);
+        if (ev_begin && ev_end && ring_ok_) cudaEventRecord(ring_[ring_count_ % kRing][0], s);
         if (after_ingest) cudaEventRecord(after_ingest, s);
         // a graph the min* rules panic on: run only the pre-check; everything else reports -2
         const int max_iter = panics_ ? 0 : (int)std::min<uint32_t>(max_it, 0x7ffffff0u);
@@ -658,6 +662,13 @@ private:
             if (!(kind_ == Kind::FloodFloat ? launch_flood_float(gl, s) : launch_layered(gl, s))) return false;
         }
         if (ev_end) cudaEventRecord(ev_[2], s);
+        if (ev_begin && ev_end && ring_ok_) {               // averaged BP-kernel time without a host sync per call (resolve_stats)
+            const size_t slot = ring_count_ % kRing;
+            if (ring_count_ - ring_resolved_ >= kRing) ++ring_resolved_;        // oldest unresolved entry is overwritten
+            cudaEventRecord(ring_[slot][1], s);
+            ring_pending_[slot] = true;
+            ++ring_count_;
+        }
         EmitLaunch em{};
         em.final_hard = ws.final_hard.p; em.n = g_.n; em.num_tiles = tiles; em.words_per_lane = nw; em.nframes = nf; em.out = d_out; em.out_len = out_len;
         em.out_stride = out_stride;
@@ -760,6 +771,22 @@ private:
 
 public:
     // resolves the event timings of the last chunk (synchronises the stream)
+    // average BP-kernel time of the passes since the previous call (up to kRing of them), and how many
+    float average_decode_ms(int64_t* launches) {
+        DeviceScope scope(device_);
+        double sum = 0;
+        int64_t n = 0;
+        for (; ring_resolved_ < ring_count_; ++ring_resolved_) {
+            const size_t slot = ring_resolved_ % kRing;
+            if (!ring_pending_[slot]) continue;
+            float ms = 0;
+            if (cudaEventSynchronize(ring_[slot][1]) == cudaSuccess && cudaEventElapsedTime(&ms, ring_[slot][0], ring_[slot][1]) == cudaSuccess) { sum += ms; ++n; }
+            ring_pending_[slot] = false;
+        }
+        if (launches) *launches = n;
+        return n ? (float)(sum / (double)n) : 0.0f;
+    }
+
     void resolve_stats() {
         if (!timed_) return;
         cudaEventSynchronize(ev_[3]);
@@ -778,6 +805,11 @@ private:
     int device_ = 0, sm_count_ = 148, max_tiles_opt_ = 0, nw_opt_ = 0;
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+    static constexpr size_t kRing = 32;
+    cudaEvent_t ring_[kRing][2] = {};
+    bool ring_pending_[kRing] = {};
+    bool ring_ok_ = false;
+    size_t ring_count_ = 0, ring_resolved_ = 0;
     bool timed_ = false;
     BatchStats stats_;
     enum class Kind { FloodI8, FloodFloat, Layered };
@@ -901,5 +933,6 @@ std::unique_ptr<LdpcDecoder> build_decoder(const DecoderImplementation& impl, co
 }
 
 void resolve_decoder_stats(LdpcDecoder* d) { static_cast<GpuDecoder*>(d)->resolve_stats(); }
+float average_decode_ms(LdpcDecoder* d, int64_t* launches) { return static_cast<GpuDecoder*>(d)->average_decode_ms(launches); }
 
 }  // namespace ldpc

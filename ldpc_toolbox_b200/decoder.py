@@ -129,6 +129,12 @@ class Decoder:
         if self._lib.ldpc_toolbox_decoder_wait(self._h, ticket) != 0:
             raise RuntimeError(f"wait: {capi.last_error()}")
 
+    def average_decode_ms(self):
+        """(average BP-kernel ms, launches) over the launches since the previous call (at most the last 32)."""
+        n = C.c_int64(0)
+        ms = self._lib.ldpc_toolbox_decoder_average_decode_ms(self._h, C.byref(n))
+        return float(ms), int(n.value)
+
     def last_timing(self):
         ms = (C.c_float * 3)()
         launches = self._lib.ldpc_toolbox_decoder_last_timing(self._h, ms)
