@@ -67,10 +67,11 @@ FLOAT_AT_SCALE = [
     ("ar4ja:1/2:1024", "Tanhf32", 1.6, 50, 8192, 1),
     ("ar4ja:1/2:1024", "Tanhf64", 1.6, 50, 8192, 0),
     # f32 phi(x) = -ln(tanh(x/2)) is ill-conditioned where tanh rounds towards 1 (one ulp of tanhf moves phi by up to
-    # 6 %), so libdevice-vs-glibc differences flip frames that are about to fail: 3 of 8192 at FER 3e-3; the same
-    # rule at an operating point without marginal frames must agree on every word
-    ("ar4ja:1/2:1024", "Phif32", 1.6, 50, 8192, 4),
+    # 6 %): with libdevice's tanhf / logf 3 of 8192 frames differed at FER 3e-3.  The f32 Phi rule therefore runs
+    # bit-exact ports of glibc's tanhf / logf (rules.cuh) and must agree on EVERY word and iteration count.
+    ("ar4ja:1/2:1024", "Phif32", 1.6, 50, 8192, 0),
     ("ar4ja:1/2:1024", "Phif32", 2.6, 50, 8192, 0),
+    ("nr5g:2:96", "HLPhif32", 1.0, 30, 8192, 0),
     ("ar4ja:1/2:1024", "Minstarapproxf64", 1.6, 50, 8192, 0),
     ("ar4ja:1/2:1024", "Aminstarf64", 1.6, 50, 8192, 0),
     # f32 min* rules: ln(1 + e^-t) is a fast polynomial on the GPU (rules.cuh softplus_neg), gated by these
@@ -100,5 +101,5 @@ def test_float_words_at_scale(oracle, code, impl, ebn0, max_iter, frames, allowe
     out, its = Decoder(alist, impl, punct).decode_batch(llrs, max_iter, output_len=k)
     differs = (out != rout).any(axis=1)
     assert differs.sum() <= allowed, f"{impl}: {int(differs.sum())} of {frames} words differ"
-    assert (its != rits).sum() <= max(8 * allowed, allowed), f"{impl}: {int((its != rits).sum())} iteration counts differ"
+    assert (its != rits).sum() <= 8 * allowed, f"{impl}: {int((its != rits).sum())} iteration counts differ"
     assert (rits > 0).sum() > frames // 2

@@ -10,7 +10,8 @@ Stated tolerances, relative to max(|reference|, 1), on frames whose word and ite
                         ill-conditioned where the product of tanh values rounds towards 1 in f32
   Phi:                  99 % within 1e-4 (f32) / 1e-12 (f64) and no bound on the rest: phi(sum - phi_j) cancels
                         catastrophically when one input dominates the sum, so one ulp of difference in a libm result
-                        moves a few isolated messages by O(1) in BOTH implementations' own arithmetic (the words still agree)
+                        moves a few isolated messages by O(1) in BOTH implementations' own arithmetic (the words still
+                        agree).  (The f32 rule has since been given bit-exact ports of glibc's tanhf / logf, rules.cuh.)
 Measured on a B200 (tests/posterior_probe.py): 256 of 256 frames match for all 16 names; maxima 1.4e-5 / 5e-14
 (Min*-approx), 8.6e-6 / 1.3e-14 (A-Min*), 2.8e-3 / 1.7e-11 (Tanh)."""
 import numpy as np
