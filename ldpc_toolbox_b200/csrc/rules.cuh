@@ -21,132 +21,7 @@ constexpr int kRuleMaxD = 32;        // largest check degree handled by the gene
 enum RuleId { kPhi = 0, kTanh = 1, kMinstarapprox = 2, kAminstar = 3 };
 
 
-// ---- bit-exact ports of the two glibc 2.39 float functions the f32 Phi rule calls ---------------------------------
-// phi(x) = -ln(tanh(x/2)) is ill-conditioned in f32 where tanh rounds towards 1: one ulp of tanhf moves phi by up to
-// 6 %, so libdevice's tanhf / logf (1-2 ulp from glibc's) flipped 3 of 8192 frames at FER 3e-3.  The reference calls
-// the platform libm (Rust f32::tanh / f32::ln -> tanhf / logf); on this platform that is glibc 2.39, whose
-//   tanhf  = fdlibm's float tanh on top of fdlibm's expm1f (pure f32 arithmetic, no tables), and
-//   logf   = the table-driven double-precision algorithm of ARM's optimized routines (16-entry table, cubic),
-// restated here with every operation rounded exactly as the C code does (no FMA contraction: __f*_rn / __d*_rn).
-// Both were compared with the system libm on EVERY float of their domain of use before going to the GPU
-// (tanhf: all 880 803 841 floats in [2^-100, 32]; logf: all 1 115 684 864 floats in (0, 64]): zero mismatches.
-__device__ __forceinline__ float glibc_expm1f(float x) {
-    const float one = 1.0f, huge = 1.0e+30f, tiny = 1.0e-30f, o_threshold = 8.8721679688e+01f, ln2_hi = 6.9313812256e-01f,
-                ln2_lo = 9.0580006145e-06f, invln2 = 1.4426950216e+00f, Q1 = -3.3333335072e-02f, Q2 = 1.5873016091e-03f,
-                Q3 = -7.9365076090e-05f, Q4 = 4.0082177293e-06f, Q5 = -2.0109921195e-07f;
-    float y, hi, lo, c = 0.0f, t, e, hxs, hfx, r1;
-    int k;
-    uint32_t hx = __float_as_uint(x);
-    const uint32_t xsb = hx & 0x80000000u;
-    hx &= 0x7fffffffu;
-    if (hx >= 0x4195b844u) {                         // |x| >= 27 ln2
-        if (hx >= 0x42b17218u) {
-            if (hx > 0x7f800000u) return __fadd_rn(x, x);
-            if (hx == 0x7f800000u) return xsb == 0 ? x : -1.0f;
-            if (x > o_threshold) return __fmul_rn(huge, huge);
-        }
-        if (xsb != 0) return __fsub_rn(tiny, one);
-    }
-    if (hx > 0x3eb17218u) {                          // |x| > 0.5 ln2
-        if (hx < 0x3F851592u) {                      // |x| < 1.5 ln2
-            if (xsb == 0) { hi = __fsub_rn(x, ln2_hi); lo = ln2_lo; k = 1; }
-            else { hi = __fadd_rn(x, ln2_hi); lo = -ln2_lo; k = -1; }
-        } else {
-            k = __float2int_rz(__fadd_rn(__fmul_rn(invln2, x), xsb == 0 ? 0.5f : -0.5f));
-            t = (float)k;
-            hi = __fsub_rn(x, __fmul_rn(t, ln2_hi));
-            lo = __fmul_rn(t, ln2_lo);
-        }
-        x = __fsub_rn(hi, lo);
-        c = __fsub_rn(__fsub_rn(hi, x), lo);
-    } else if (hx < 0x33000000u) {                   // |x| < 2^-25
-        t = __fadd_rn(huge, x);
-        return __fsub_rn(x, __fsub_rn(t, __fadd_rn(huge, x)));
-    } else {
-        k = 0;
-    }
-    hfx = __fmul_rn(0.5f, x);
-    hxs = __fmul_rn(x, hfx);
-    r1 = __fadd_rn(one, __fmul_rn(hxs, __fadd_rn(Q1, __fmul_rn(hxs, __fadd_rn(Q2, __fmul_rn(hxs, __fadd_rn(Q3, __fmul_rn(hxs, __fadd_rn(Q4, __fmul_rn(hxs, Q5))))))))));
-    t = __fsub_rn(3.0f, __fmul_rn(r1, hfx));
-    e = __fmul_rn(hxs, __fdiv_rn(__fsub_rn(r1, t), __fsub_rn(6.0f, __fmul_rn(x, t))));
-    if (k == 0) return __fsub_rn(x, __fsub_rn(__fmul_rn(x, e), hxs));
-    e = __fsub_rn(__fmul_rn(x, __fsub_rn(e, c)), c);
-    e = __fsub_rn(e, hxs);
-    if (k == -1) return __fsub_rn(__fmul_rn(0.5f, __fsub_rn(x, e)), 0.5f);
-    if (k == 1) {
-        if (x < -0.25f) return __fmul_rn(-2.0f, __fsub_rn(e, __fadd_rn(x, 0.5f)));
-        return __fadd_rn(one, __fmul_rn(2.0f, __fsub_rn(x, e)));
-    }
-    if (k <= -2 || k > 56) {
-        y = __fsub_rn(one, __fsub_rn(e, x));
-        y = __uint_as_float(__float_as_uint(y) + ((uint32_t)k << 23));
-        return __fsub_rn(y, one);
-    }
-    if (k < 23) {
-        t = __uint_as_float(0x3f800000u - (0x1000000u >> k));
-        y = __fsub_rn(t, __fsub_rn(e, x));
-        y = __uint_as_float(__float_as_uint(y) + ((uint32_t)k << 23));
-    } else {
-        t = __uint_as_float((uint32_t)(0x7f - k) << 23);
-        y = __fsub_rn(x, __fadd_rn(e, t));
-        y = __fadd_rn(y, one);
-        y = __uint_as_float(__float_as_uint(y) + ((uint32_t)k << 23));
-    }
-    return y;
-}
-
-__device__ __forceinline__ float glibc_tanhf(float x) {
-    const float one = 1.0f, tiny = 1.0e-30f;
-    const uint32_t jx = __float_as_uint(x), ix = jx & 0x7fffffffu;
-    float t, z;
-    if (!(ix < 0x7f800000u)) return (int32_t)jx >= 0 ? __fadd_rn(__fdiv_rn(one, x), one) : __fsub_rn(__fdiv_rn(one, x), one);
-    if (ix < 0x41b00000u) {                          // |x| < 22
-        if (ix == 0) return x;
-        if (ix < 0x24000000u) return __fmul_rn(x, __fadd_rn(one, x));
-        if (ix >= 0x3f800000u) {                     // |x| >= 1
-            t = glibc_expm1f(__fmul_rn(2.0f, fabsf(x)));
-            z = __fsub_rn(one, __fdiv_rn(2.0f, __fadd_rn(t, 2.0f)));
-        } else {
-            t = glibc_expm1f(__fmul_rn(-2.0f, fabsf(x)));
-            z = __fdiv_rn(-t, __fadd_rn(t, 2.0f));
-        }
-    } else {
-        z = __fsub_rn(one, tiny);
-    }
-    return (int32_t)jx >= 0 ? z : -z;
-}
-
-// {1/c, ln c} for the 16 sub-intervals of [0.7, 1.4) and the cubic of ln(1 + r) — glibc's __logf_data
-__device__ const double kGlibcLogfTab[32] = {
-    0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2, 0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2, 0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2,
-    0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3, 0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3, 0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3,
-    0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4, 0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4, 0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5,
-    0x1p+0, 0x0p+0, 0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5, 0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4,
-    0x1.b2036576afce6p-1, 0x1.526e57720db08p-3, 0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3, 0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2,
-    0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2};
-
-__device__ __forceinline__ float glibc_logf(float x) {
-    const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2, Ln2 = 0x1.62e42fefa39efp-1;
-    uint32_t ix = __float_as_uint(x);
-    if (ix == 0x3f800000u) return 0.0f;
-    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
-        if (ix * 2 == 0) return -CUDART_INF_F;
-        if (ix == 0x7f800000u) return x;
-        if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return CUDART_NAN_F;
-        ix = __float_as_uint(__fmul_rn(x, 0x1p23f));  // subnormal: normalise
-        ix -= 23u << 23;
-    }
-    const uint32_t tmp = ix - 0x3f330000u;
-    const int i = (int)((tmp >> 19) & 15u), k = (int32_t)tmp >> 23;
-    const uint32_t iz = ix - (tmp & 0xff800000u);
-    const double invc = __ldg(&kGlibcLogfTab[2 * i]), logc = __ldg(&kGlibcLogfTab[2 * i + 1]), z = (double)__uint_as_float(iz);
-    const double r = __dadd_rn(__dmul_rn(z, invc), -1.0), y0 = __dadd_rn(logc, __dmul_rn((double)k, Ln2)), r2 = __dmul_rn(r, r);
-    double y = __dadd_rn(__dmul_rn(A1, r), A2);
-    y = __dadd_rn(__dmul_rn(A0, r2), y);
-    y = __dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r));
-    return __double2float_rn(y);
-}
+#include "libm_exact.h"
 
 template <class F> struct FMath;
 template <> struct FMath<float> {
@@ -156,8 +31,8 @@ template <> struct FMath<float> {
     static __device__ __forceinline__ float phi_tanh_(float x) { return tanhf(x); }
     static __device__ __forceinline__ float phi_log_(float x) { return logf(x); }
 #else
-    static __device__ __forceinline__ float phi_tanh_(float x) { return glibc_tanhf(x); }      // bit-exact with the reference's libm
-    static __device__ __forceinline__ float phi_log_(float x) { return glibc_logf(x); }
+    static __device__ __forceinline__ float phi_tanh_(float x) { return libm_exact_tanhf(x); }      // bit-exact with the reference's libm
+    static __device__ __forceinline__ float phi_log_(float x) { return libm_exact_logf(x); }
 #endif
     static __device__ __forceinline__ float exp_(float x) { return expf(x); }
     static __device__ __forceinline__ float log1p_(float x) { return log1pf(x); }

@@ -1,0 +1,28 @@
+/* tests/libm_port_check.c — host check of ldpc_toolbox_b200/csrc/libm_exact.h (test infrastructure): the very text the
+ * GPU compiles, built here with plain operators and -ffp-contract=off, against the system libm on every float of the
+ * domain the f32 Phi rule uses.  Prints the mismatch counts; tests/test_libm_ports.py asserts they are zero.
+ *   gcc -O2 -ffp-contract=off -fopenmp tests/libm_port_check.c -o check -lm && ./check [stride] */
+#include <stdio.h>
+#include <stdlib.h>
+#include "../ldpc_toolbox_b200/csrc/libm_exact.h"
+
+int main(int argc, char** argv) {
+    const uint32_t stride = argc > 1 ? (uint32_t)atoi(argv[1]) : 1u;
+    long bad_tanh = 0, bad_log = 0, n_tanh = 0, n_log = 0;
+    const uint32_t t_lo = lme_f2u(0x1p-100f), t_hi = lme_f2u(32.0f), l_hi = lme_f2u(64.0f);
+#pragma omp parallel for reduction(+ : bad_tanh, n_tanh) schedule(static)
+    for (uint32_t u = t_lo; u <= t_hi; u += stride) {
+        const float x = lme_u2f(u);
+        bad_tanh += lme_f2u(tanhf(x)) != lme_f2u(libm_exact_tanhf(x));
+        bad_tanh += lme_f2u(tanhf(-x)) != lme_f2u(libm_exact_tanhf(-x));
+        ++n_tanh;
+    }
+#pragma omp parallel for reduction(+ : bad_log, n_log) schedule(static)
+    for (uint32_t u = 1; u <= l_hi; u += stride) {
+        const float x = lme_u2f(u);
+        bad_log += lme_f2u(logf(x)) != lme_f2u(libm_exact_logf(x));
+        ++n_log;
+    }
+    printf("{\"tanhf_checked\": %ld, \"tanhf_mismatches\": %ld, \"logf_checked\": %ld, \"logf_mismatches\": %ld}\n", n_tanh, bad_tanh, n_log, bad_log);
+    return bad_tanh || bad_log;
+}
