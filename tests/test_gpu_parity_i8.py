@@ -138,6 +138,45 @@ def test_two_lane_pipeline_and_submit_wait(oracle):
     assert (h_it.numpy() == rits).all() and (h_out.numpy() == rout).all()
 
 
+@pytest.mark.parametrize("nw", ["1", "4"])
+@pytest.mark.parametrize("code,ebn0", [("dvbs2:R3_5short", 1.8), ("dvbs2:R8_9short", 4.0)])
+@pytest.mark.parametrize("impl", ["Minstarapproxi8", "Minstarapproxi8JonesPartialHardLimitDeg1Clip", "Aminstari8", "Aminstari8JonesPartialHardLimit"])
+def test_wide_row_kernels_on_dvbs2_high_rates(oracle, impl, code, ebn0, nw, monkeypatch):
+    """Check degrees 11 (one 16-line stage per warp) and 27 (32-line stage): rows folded from shared memory by
+    check_wide, for both rule families and the clipping variants, on 128- and 512-frame tiles."""
+    monkeypatch.setenv("LDPC_B200_NW", nw)
+    alist = codes.alist_for(code)
+    first = alist.split("\n", 1)[0].split()
+    n, k = int(first[0]), int(first[0]) - int(first[1])
+    rng = np.random.default_rng(zlib.crc32(f"{impl}{code}{nw}".encode()))
+    enc = oracle.encoder(alist)
+    msgs, cws = helpers.encoded_frames(enc, rng, k, n, 8)
+    llrs = np.concatenate([helpers.awgn_llrs(rng, cws[np.arange(40) % 8], helpers.sigma_for(e, k / n)) for e in (ebn0 - 0.5, ebn0 + 0.3)])
+    its = compare(oracle, alist, impl, llrs, 20, out_len=k, label=f"{code} nw {nw} ")
+    assert (its > 0).any()
+
+
+def test_async_api_edge_cases(oracle):
+    """Empty batches, tickets waited twice / out of range, posterior hook on an unsupported decoder."""
+    rng = np.random.default_rng(3)
+    alist = helpers.random_code_alist(rng, 60, 30)
+    dec = Decoder(alist, "Minstarapproxi8")
+    llrs = helpers.awgn_llrs(rng, np.zeros((5, 60), dtype=np.uint8), 0.8)
+    out = np.zeros((5, 60), dtype=np.uint8)
+    it = np.zeros(5, dtype=np.int32)
+    t0 = dec.submit_batch_ptr(llrs.ctypes.data, False, 60, 0, 10, out.ctypes.data, 60, 60, it.ctypes.data)      # nothing to do
+    t1 = dec.submit_batch_ptr(llrs.ctypes.data, False, 60, 5, 10, out.ctypes.data, 60, 60, it.ctypes.data)      # pageable buffers work too
+    dec.wait(t1)
+    dec.wait(t0)                                   # already retired: a no-op
+    dec.wait(t1)
+    rout, rits = oracle.decoder(alist, "Minstarapproxi8").decode_batch(llrs, 10)
+    assert (it == rits).all() and (out == rout).all()
+    with pytest.raises(ValueError):
+        dec.submit_batch_ptr(llrs.ctypes.data, False, 59, 5, 10, out.ctypes.data, 60, 60, it.ctypes.data)       # wrong llrs_len
+    with pytest.raises(ValueError):
+        dec.decode_batch_posteriors(llrs, 10)                                                                       # int8 decoder
+
+
 def test_ragged_batch_and_strides(oracle):
     rng = np.random.default_rng(5)
     alist = helpers.random_code_alist(rng, 120, 60)
