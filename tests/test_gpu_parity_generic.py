@@ -1,8 +1,9 @@
 """GPU parity for K2 (float flooding) and K3 (horizontal layered) against the CPU checker, through
 the C-ABI.  int8 layered decoders: bit-exact words and iteration counts.  Float decoders: the
-transcendental functions come from libdevice instead of the host libm, so parity is statistical —
-the decoded word and iteration count must agree on (nearly) every frame (BASELINE.json: >= 99.99 %
-of frames at scale; here at most a stated handful out of each small sample).  Needs a B200."""
+transcendental functions come from libdevice instead of the host libm (except the f32 Phi rule, which runs
+bit-exact ports of glibc's tanhf / logf), so parity is statistical — the decoded word and iteration count
+must agree on (nearly) every frame (BASELINE.json: >= 99.99 % of frames; at scale in test_gpu_parity_scale.py,
+here at most ONE frame of each 800-frame sample, none for f64 and Phi).  Needs a B200."""
 import numpy as np
 import pytest
 
@@ -56,7 +57,9 @@ def test_layered_float_smem_path_small_codes(oracle, impl, monkeypatch):
         nbad, its, rits = run_pair(oracle, alist, impl, llrs, 12)
         bad += nbad
         total += len(its)
-    assert bad <= (2 if impl.endswith("f64") else 8), f"{impl}: {bad} of {total} frames differ from the CPU checker"
+    # measured: 0 of 800 for every name (tools/float_small_code_counts.py); one last-ulp flip is tolerated for the f32
+    # rules that still use libdevice transcendentals, none for f64 and for the bit-exact f32 Phi rule
+    assert bad <= (0 if impl.endswith("f64") or "Phi" in impl else 1), f"{impl}: {bad} of {total} frames differ from the CPU checker"
 
 
 def test_layered_smem_punctured_f64_input_and_zero_iterations(oracle, monkeypatch):
@@ -70,7 +73,7 @@ def test_layered_smem_punctured_f64_input_and_zero_iterations(oracle, monkeypatc
     llrs = helpers.awgn_llrs(rng, tx, helpers.sigma_for(1.8, 0.5), np.float64)
     for impl, iters in (("HLMinstarapproxi8", 30), ("HLAminstari8", 0), ("HLPhif64", 20)):
         nbad, its, rits = run_pair(oracle, alist, impl, llrs, iters, puncturing="1,1,1,1,0", out_len=1024)
-        assert nbad <= (1 if impl.endswith("f64") else 0), (impl, nbad)
+        assert nbad == 0, (impl, nbad)
 
 
 @pytest.mark.parametrize("impl", FLOAT_FLOOD + HL_FLOAT)
@@ -81,8 +84,9 @@ def test_float_rules_small_codes(oracle, impl):
         bad += nbad
         total += len(its)
         assert (its > 0).any()
-    # f64: only last-ulp libm differences; f32: same plus tanh/atanh conditioning near saturation
-    limit = 2 if impl.endswith("f64") else 8
+    # measured: 0 of 800 for every name (tools/float_small_code_counts.py).  f64: none tolerated; f32 rules on libdevice
+    # transcendentals (Tanh, Min*-approx, A-Min*): one last-ulp flip; the f32 Phi rule runs bit-exact libm ports: none
+    limit = 0 if impl.endswith("f64") or "Phi" in impl else 1
     assert bad <= limit, f"{impl}: {bad} of {total} frames differ from the CPU checker"
 
 
