@@ -1,4 +1,5 @@
-// ldpc_toolbox_b200/csrc/libm_exact.h — bit-exact ports of the two glibc 2.39 float functions the f32 Phi rule calls.
+// ldpc_toolbox_b200/csrc/libm_exact.h — bit-exact ports of the glibc 2.39 float functions the f32 Phi and Tanh rules call
+// (tanhf, logf; atanhf over log1pf at the end of the file).
 //
 // phi(x) = -ln(tanh(x/2)) is ill-conditioned in f32 where tanh rounds towards 1: one ulp of tanhf moves phi by up to
 // 6 %, so libdevice's tanhf / logf (1-2 ulp from glibc's) flipped 3 of 8192 frames at FER 3e-3.  The reference calls
@@ -172,4 +173,85 @@ LME_FN float libm_exact_logf(float x) {
     y = LME_DADD(LME_DMUL(A0, r2), y);
     y = LME_DADD(LME_DMUL(y, r2), LME_DADD(y0, r));
     return LME_D2F(y);
+}
+
+// ---- atanhf (glibc 2.39: sysdeps/ieee754/flt-32/e_atanhf.c on top of fdlibm's s_log1pf.c), used by the f32 Tanh rule
+// (reference src/decoder/arithmetic.rs:347-379: 2 atanh(prod of tanh)).  Same conventions as above.
+LME_FN float libm_exact_log1pf(float x) {
+    const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f, two25 = 3.355443200e+07f, Lp1 = 6.6666668653e-01f,
+                Lp2 = 4.0000000596e-01f, Lp3 = 2.8571429849e-01f, Lp4 = 2.2222198546e-01f, Lp5 = 1.8183572590e-01f,
+                Lp6 = 1.5313838422e-01f, Lp7 = 1.4798198640e-01f, zero = 0.0f;
+    float hfsq, f = 0.0f, c = 0.0f, s, z, R, u;
+    int32_t k, hx, hu = 0, ax;
+    hx = (int32_t)LME_F2U(x);
+    ax = hx & 0x7fffffff;
+    k = 1;
+    if (hx < 0x3ed413d7) {                           // x < 0.41422
+        if (ax >= 0x3f800000) {                      // x <= -1.0
+            if (x == -1.0f) return LME_FDIV(-two25, zero);
+            return LME_FDIV(LME_FSUB(x, x), LME_FSUB(x, x));
+        }
+        if (ax < 0x31000000) {                       // |x| < 2^-29
+            if (ax < 0x24800000) return x;           // |x| < 2^-54
+            return LME_FSUB(x, LME_FMUL(LME_FMUL(x, x), 0.5f));
+        }
+        if (hx > 0 || hx <= (int32_t)0xbe95f61f) { k = 0; f = x; hu = 1; }      // -0.2929 < x < 0.41422
+    }
+    if (hx >= 0x7f800000) return LME_FADD(x, x);
+    if (k != 0) {
+        if (hx < 0x5a000000) {
+            u = LME_FADD(1.0f, x);
+            hu = (int32_t)LME_F2U(u);
+            k = (hu >> 23) - 127;
+            c = (k > 0) ? LME_FSUB(1.0f, LME_FSUB(u, x)) : LME_FSUB(x, LME_FSUB(u, 1.0f));      // correction term
+            c = LME_FDIV(c, u);
+        } else {
+            u = x;
+            hu = (int32_t)LME_F2U(u);
+            k = (hu >> 23) - 127;
+            c = 0.0f;
+        }
+        hu &= 0x007fffff;
+        if (hu < 0x3504f7) {
+            u = LME_U2F((uint32_t)hu | 0x3f800000u);          // normalize u
+        } else {
+            k += 1;
+            u = LME_U2F((uint32_t)hu | 0x3f000000u);          // normalize u/2
+            hu = (0x00800000 - hu) >> 2;
+        }
+        f = LME_FSUB(u, 1.0f);
+    }
+    hfsq = LME_FMUL(LME_FMUL(0.5f, f), f);
+    if (hu == 0) {                                   // |f| < 2^-20
+        if (f == zero) {
+            if (k == 0) return zero;
+            c = LME_FADD(c, LME_FMUL((float)k, ln2_lo));
+            return LME_FADD(LME_FMUL((float)k, ln2_hi), c);
+        }
+        R = LME_FMUL(hfsq, LME_FSUB(1.0f, LME_FMUL(0.66666666666666666f, f)));
+        if (k == 0) return LME_FSUB(f, R);
+        return LME_FSUB(LME_FMUL((float)k, ln2_hi), LME_FSUB(LME_FSUB(R, LME_FADD(LME_FMUL((float)k, ln2_lo), c)), f));
+    }
+    s = LME_FDIV(f, LME_FADD(2.0f, f));
+    z = LME_FMUL(s, s);
+    R = LME_FMUL(z, LME_FADD(Lp1, LME_FMUL(z, LME_FADD(Lp2, LME_FMUL(z, LME_FADD(Lp3, LME_FMUL(z, LME_FADD(Lp4, LME_FMUL(z, LME_FADD(Lp5, LME_FMUL(z, LME_FADD(Lp6, LME_FMUL(z, Lp7)))))))))))));
+    if (k == 0) return LME_FSUB(f, LME_FSUB(hfsq, LME_FMUL(s, LME_FADD(hfsq, R))));
+    return LME_FSUB(LME_FMUL((float)k, ln2_hi),
+                    LME_FSUB(LME_FSUB(hfsq, LME_FADD(LME_FMUL(s, LME_FADD(hfsq, R)), LME_FADD(LME_FMUL((float)k, ln2_lo), c))), f));
+}
+
+LME_FN float libm_exact_atanhf(float x) {
+    const float xa = LME_FABS(x);
+    float t;
+    if (xa < 0.5f) {
+        if (xa < 0x1.0p-28f) return x;
+        t = LME_FADD(xa, xa);
+        t = LME_FMUL(0.5f, libm_exact_log1pf(LME_FADD(t, LME_FDIV(LME_FMUL(t, xa), LME_FSUB(1.0f, xa)))));
+    } else if (xa < 1.0f) {
+        t = LME_FMUL(0.5f, libm_exact_log1pf(LME_FDIV(LME_FADD(xa, xa), LME_FSUB(1.0f, xa))));
+    } else {
+        if (xa > 1.0f) return LME_FDIV(LME_FSUB(x, x), LME_FSUB(x, x));
+        return LME_FDIV(x, 0.0f);
+    }
+    return LME_U2F((LME_F2U(t) & 0x7fffffffu) | (LME_F2U(x) & 0x80000000u));
 }

@@ -25,7 +25,14 @@ enum RuleId { kPhi = 0, kTanh = 1, kMinstarapprox = 2, kAminstar = 3 };
 
 template <class F> struct FMath;
 template <> struct FMath<float> {
+#ifdef LDPC_LIBDEVICE_TANH
     static __device__ __forceinline__ float tanh_(float x) { return tanhf(x); }
+    static __device__ __forceinline__ float atanh_(float x) { return atanhf(x); }
+#else
+    // the f32 Tanh rule (2 atanh of a product of tanh values near +-1) gets the same bit-exact libm ports as Phi
+    static __device__ __forceinline__ float tanh_(float x) { return libm_exact_tanhf(x); }
+    static __device__ __forceinline__ float atanh_(float x) { return libm_exact_atanhf(x); }
+#endif
     static __device__ __forceinline__ float log_(float x) { return logf(x); }
 #ifdef LDPC_LIBDEVICE_PHI
     static __device__ __forceinline__ float phi_tanh_(float x) { return tanhf(x); }
@@ -36,7 +43,6 @@ template <> struct FMath<float> {
 #endif
     static __device__ __forceinline__ float exp_(float x) { return expf(x); }
     static __device__ __forceinline__ float log1p_(float x) { return log1pf(x); }
-    static __device__ __forceinline__ float atanh_(float x) { return atanhf(x); }
     static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
     static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
     static __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }

@@ -23,6 +23,16 @@ int main(int argc, char** argv) {
         bad_log += lme_f2u(logf(x)) != lme_f2u(libm_exact_logf(x));
         ++n_log;
     }
+    long bad_atanh = 0, n_atanh = 0;
+    const uint32_t a_hi = lme_f2u(1.0f);
+#pragma omp parallel for reduction(+ : bad_atanh, n_atanh) schedule(static)
+    for (uint32_t u = 0; u <= a_hi; u += stride) {
+        const float x = lme_u2f(u);
+        bad_atanh += lme_f2u(atanhf(x)) != lme_f2u(libm_exact_atanhf(x));
+        bad_atanh += lme_f2u(atanhf(-x)) != lme_f2u(libm_exact_atanhf(-x));
+        ++n_atanh;
+    }
+    printf("{\"atanhf_checked\": %ld, \"atanhf_mismatches\": %ld}\n", n_atanh, bad_atanh);
     printf("{\"tanhf_checked\": %ld, \"tanhf_mismatches\": %ld, \"logf_checked\": %ld, \"logf_mismatches\": %ld}\n", n_tanh, bad_tanh, n_log, bad_log);
-    return bad_tanh || bad_log;
+    return bad_tanh || bad_log || bad_atanh;
 }

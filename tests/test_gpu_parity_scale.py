@@ -64,7 +64,7 @@ def test_north_star_bench_kernel_shape_16k_frames(oracle, monkeypatch):
 # frames, so the bound is 1 frame (a single last-ulp tie) for the rules whose transcendentals differ between
 # libdevice and glibc, 0 for f64.
 FLOAT_AT_SCALE = [
-    ("ar4ja:1/2:1024", "Tanhf32", 1.6, 50, 8192, 1),
+    ("ar4ja:1/2:1024", "Tanhf32", 1.6, 50, 8192, 0),        # bit-exact libm ports (tanhf, atanhf), like Phif32 below
     ("ar4ja:1/2:1024", "Tanhf64", 1.6, 50, 8192, 0),
     # f32 phi(x) = -ln(tanh(x/2)) is ill-conditioned where tanh rounds towards 1 (one ulp of tanhf moves phi by up to
     # 6 %): with libdevice's tanhf / logf 3 of 8192 frames differed at FER 3e-3.  The f32 Phi rule therefore runs
@@ -80,7 +80,7 @@ FLOAT_AT_SCALE = [
     ("nr5g:2:384", "HLMinstarapproxf32", 0.25, 50, 8192, 1),        # BASELINE configs[1]
     ("nr5g:1:384", "Aminstarf32", 0.75, 50, 4096, 1),               # BASELINE configs[3], flooding
     ("nr5g:1:384", "HLAminstarf32", 0.75, 50, 4096, 1),             # BASELINE configs[3], layered
-    ("nr5g:2:96", "HLTanhf32", 1.0, 30, 8192, 1),
+    ("nr5g:2:96", "HLTanhf32", 1.0, 30, 8192, 0),
     ("nr5g:2:96", "HLPhif64", 1.0, 30, 8192, 0),
 ]
 
