@@ -158,6 +158,7 @@ public:
         nw_opt_ = opt.words_per_lane;
         if (const char* e = getenv("LDPC_B200_NW")) nw_opt_ = atoi(e);
         if (const char* e = getenv("LDPC_B200_TWO_STAGE")) two_stage_ = atoi(e) != 0;
+        if (const char* e = getenv("LDPC_B200_EXACT_LIBM")) exact_libm_ = atoi(e) != 0;
         return true;
     }
 
@@ -338,6 +339,17 @@ private:
         if (kind_ != Kind::FloodI8) return 1;
         if (nw_opt_ == 1 || nw_opt_ == 4) return nw_opt_;
         return nframes >= (size_t)sm_count_ * 512 ? 4 : 1;
+    }
+
+    // rules.cuh rule id; LDPC_B200_EXACT_LIBM=1 selects the bit-exact ln(1 + e^-t) for the f32 Min*-approx / A-Min* rules
+    int rule_id() const {
+        const bool exact = exact_libm_ && impl_.dtype == Dtype::F32;
+        switch (impl_.rule) {
+            case Rule::Phi: return kPhi;
+            case Rule::Tanh: return kTanh;
+            case Rule::Minstarapprox: return exact ? kMinstarapproxExact : kMinstarapprox;
+            default: return exact ? kAminstarExact : kAminstar;
+        }
     }
 
     // HBM bytes of decoder state per 128 frames
@@ -568,7 +580,7 @@ private:
         cudaEventRecord(ev_[1], s);
         LayeredSmemLaunch L{};
         L.graph = sg_;
-        L.rule = impl_.rule == Rule::Phi ? kPhi : impl_.rule == Rule::Tanh ? kTanh : impl_.rule == Rule::Minstarapprox ? kMinstarapprox : kAminstar;
+        L.rule = rule_id();
         L.is_f64 = impl_.dtype == Dtype::F64; L.is_i8 = impl_.dtype == Dtype::I8; L.hardlimit = impl_.hardlimit;
         L.threads = smem_threads_;
         L.llrs = d_llrs; L.in_f64 = is_f64; L.llrs_len = llrs_len; L.nframes = nf; L.src_map = punct_ ? d_src_map_.p : nullptr;
@@ -651,7 +663,7 @@ private:
             GenericLaunch gl{};
             gl.graph = dg_; gl.num_tiles = tiles; gl.is_f64 = impl_.dtype == Dtype::F64; gl.is_i8 = impl_.dtype == Dtype::I8;
             gl.hardlimit = impl_.hardlimit;
-            gl.rule = impl_.rule == Rule::Phi ? kPhi : impl_.rule == Rule::Tanh ? kTanh : impl_.rule == Rule::Minstarapprox ? kMinstarapprox : kAminstar;
+            gl.rule = rule_id();
             gl.msg = ws.msg.p; gl.hbit = ws.hbit.p; gl.in = ws.inq.p; gl.in_out_q = ws.inq.p;
             gl.raw0 = ws.hard.p; gl.final_hard = ws.final_hard.p; gl.iters = ws.iters_tile.p; gl.max_iter = max_iter;
             gl.level_ptr = d_level_ptr_.p; gl.level_rows = d_level_rows_.p; gl.num_levels = num_levels_;
@@ -841,6 +853,7 @@ private:
     DevBuf<unsigned int> d_hist_;
     unsigned int* h_hist_ = nullptr;
     cudaEvent_t ev_hist_ = nullptr;
+    bool exact_libm_ = false;
     bool two_stage_ = false, hist_valid_ = false;      // opt-in (LDPC_B200_TWO_STAGE=1): exact, but measured no faster on DVB-S2
     uint32_t hist_max_it_ = 0;
     long long two_stage_chunks_ = 0;

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kGWarps * 32, sizeof(F) == 8 ? 1 : 2) flood_fl
             if (last || d == 0) continue;
             // O(d) rules are unrolled up to degree 20 (5G-NR base graph 1 has rows of degree 19), the
             // O(d^2) transcendental fold of Min*-approx up to 10
-            constexpr int kUnrollMax = (RULE == kMinstarapprox || sizeof(F) == 8) ? 10 : 20;     // (f64: code size / build time)
+            constexpr int kUnrollMax = (rule_is_minstar(RULE) || sizeof(F) == 8) ? 10 : 20;     // (f64: code size / build time)
 #define LDPC_CHK_CASE(D_) case D_: flood_check_row<F, RULE, (D_ <= kUnrollMax ? D_ : 0)>(msg, (size_t)e0, d, lane); break;
             switch (d) {
                 LDPC_CHK_CASE(1) LDPC_CHK_CASE(2) LDPC_CHK_CASE(3) LDPC_CHK_CASE(4) LDPC_CHK_CASE(5) LDPC_CHK_CASE(6)
@@ -277,6 +277,9 @@ static bool launch_flood_float_t(const GenericLaunch& L, cudaStream_t stream) {
         case kPhi: LDPC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, flood_float_kernel<F, kPhi>, p)); break;
         case kTanh: LDPC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, flood_float_kernel<F, kTanh>, p)); break;
         case kMinstarapprox: LDPC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, flood_float_kernel<F, kMinstarapprox>, p)); break;
+        // bit-exact libm mode: instantiated for f32 only (f64 evaluates the same expression either way)
+        case kMinstarapproxExact: LDPC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, flood_float_kernel<F, (sizeof(F) == 4 ? kMinstarapproxExact : kMinstarapprox)>, p)); break;
+        case kAminstarExact: LDPC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, flood_float_kernel<F, (sizeof(F) == 4 ? kAminstarExact : kAminstar)>, p)); break;
         default: LDPC_CUDA_CHECK(cudaLaunchKernelEx(&cfg, flood_float_kernel<F, kAminstar>, p)); break;
     }
     LDPC_CUDA_CHECK(cudaGetLastError());

@@ -7,6 +7,8 @@ bool launch_layered_smem_f32(const LayeredSmemLaunch& L, cudaStream_t stream) {
         case kPhi: return launch_t<float, kPhi, false, false>(L, stream);
         case kTanh: return launch_t<float, kTanh, false, false>(L, stream);
         case kMinstarapprox: return launch_t<float, kMinstarapprox, false, false>(L, stream);
+        case kMinstarapproxExact: return launch_t<float, kMinstarapproxExact, false, false>(L, stream);
+        case kAminstarExact: return launch_t<float, kAminstarExact, false, false>(L, stream);
         default: return launch_t<float, kAminstar, false, false>(L, stream);
     }
 }

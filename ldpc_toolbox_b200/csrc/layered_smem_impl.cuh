@@ -81,7 +81,7 @@ __device__ __forceinline__ void process_row(Q* __restrict__ qs, R* __restrict__ 
         check_rule_float<F, RULE, DT>(x, d, out, scratch);
 #pragma unroll
         for (int j = 0; j < d; ++j) {
-            if (RULE == kPhi || RULE == kAminstar) q[j] = (Q)(x[j] + out[j]);                 // :290, :1064
+            if (RULE == kPhi || rule_is_aminstar(RULE)) q[j] = (Q)(x[j] + out[j]);                 // :290, :1064
             else q[j] = (Q)((F)q[j] + (out[j] - (F)r[j]));                                    // :423, :571
             r[j] = (R)out[j];
         }
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kSmemLayeredMaxThreads, sizeof(F) == 8 ? 1 : 2
                     R* rr = rcv + off + (r - r0);
                     const int* cc = g.ell_col + off + (r - r0);
                     // O(d) rules unroll up to degree 20 (5G-NR base graph 1: rows of degree 19), the O(d^2) ones to 10
-                    constexpr int kUnrollMax = (RULE == kMinstarapprox || RULE == kTanh || sizeof(F) == 8) ? 10 : 20;
+                    constexpr int kUnrollMax = (rule_is_minstar(RULE) || RULE == kTanh || sizeof(F) == 8) ? 10 : 20;
 #define LDPC_ROW_CASE(D_) case D_: process_row<F, RULE, IS_I8, HLIM, (D_ <= kUnrollMax ? D_ : 0), Q, R>(qs, rr, cc, stride, d, first, tb); break;
                     switch (d) {
                         case 0: break;

@@ -86,7 +86,7 @@ __device__ __forceinline__ void layered_tile_row(Q* __restrict__ qv, R* __restri
             check_rule_float<F, RULE, DT>(x, d, out, scratch);
 #pragma unroll
             for (int j = 0; j < d; ++j) {
-                if (RULE == kPhi || RULE == kAminstar) qn[j] = (Q)(x[j] + out[j]);                      // :290, :1064
+                if (RULE == kPhi || rule_is_aminstar(RULE)) qn[j] = (Q)(x[j] + out[j]);                      // :290, :1064
                 else qn[j] = (Q)((F)qs[j].v[0] + (out[j] - (F)rs[j].v[0]));                             // :423, :571
                 rn[j] = (R)out[j];
             }
@@ -215,6 +215,8 @@ static bool launch_layered_t(const GenericLaunch& L, cudaStream_t stream) {
             case kPhi: layered_kernel<F, kPhi, IS_I8, false><<<grid, block, 0, stream>>>(p); break;
             case kTanh: layered_kernel<F, kTanh, IS_I8, false><<<grid, block, 0, stream>>>(p); break;
             case kMinstarapprox: layered_kernel<F, kMinstarapprox, IS_I8, false><<<grid, block, 0, stream>>>(p); break;
+            case kMinstarapproxExact: layered_kernel<F, (sizeof(F) == 4 ? kMinstarapproxExact : kMinstarapprox), IS_I8, false><<<grid, block, 0, stream>>>(p); break;
+            case kAminstarExact: layered_kernel<F, (sizeof(F) == 4 ? kAminstarExact : kAminstar), IS_I8, false><<<grid, block, 0, stream>>>(p); break;
             default: layered_kernel<F, kAminstar, IS_I8, false><<<grid, block, 0, stream>>>(p); break;
         }
     }

@@ -27,11 +27,15 @@
 #define LME_FDIV(a, b) __fdiv_rn((a), (b))
 #define LME_DADD(a, b) __dadd_rn((a), (b))
 #define LME_DMUL(a, b) __dmul_rn((a), (b))
+#define LME_DFMA(a, b, c) __fma_rn((a), (b), (c))
 #define LME_F2U(x) __float_as_uint(x)
 #define LME_U2F(x) __uint_as_float(x)
 #define LME_F2I_RZ(x) __float2int_rz(x)
 #define LME_D2F(x) __double2float_rn(x)
 #define LME_LOAD(p) __ldg(p)
+#define LME_TAB64 __device__ const unsigned long long
+#define LME_D2U(x) ((uint64_t)__double_as_longlong(x))
+#define LME_U2D(x) __longlong_as_double((long long)(x))
 #define LME_INF CUDART_INF_F
 #define LME_NAN CUDART_NAN_F
 #define LME_FABS(x) fabsf(x)
@@ -45,6 +49,7 @@
 #define LME_FDIV(a, b) ((float)((a) / (b)))
 #define LME_DADD(a, b) ((double)((a) + (b)))
 #define LME_DMUL(a, b) ((double)((a) * (b)))
+#define LME_DFMA(a, b, c) fma((a), (b), (c))
 static inline uint32_t lme_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float lme_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 #define LME_F2U(x) lme_f2u(x)
@@ -52,6 +57,11 @@ static inline float lme_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; 
 #define LME_F2I_RZ(x) ((int)(x))
 #define LME_D2F(x) ((float)(x))
 #define LME_LOAD(p) (*(p))
+#define LME_TAB64 static const unsigned long long
+static inline uint64_t lme_d2u(double d) { uint64_t u; memcpy(&u, &d, 8); return u; }
+static inline double lme_u2d(uint64_t u) { double d; memcpy(&d, &u, 8); return d; }
+#define LME_D2U(x) lme_d2u(x)
+#define LME_U2D(x) lme_u2d(x)
 #define LME_INF INFINITY
 #define LME_NAN NAN
 #define LME_FABS(x) fabsf(x)
@@ -254,4 +264,71 @@ LME_FN float libm_exact_atanhf(float x) {
         return LME_FDIV(x, 0.0f);
     }
     return LME_U2F((LME_F2U(t) & 0x7fffffffu) | (LME_F2U(x) & 0x80000000u));
+}
+
+// ---- expf (glibc 2.39: sysdeps/ieee754/flt-32/e_expf.c, ARM optimized routines: 2^(k/32) table, cubic in double),
+// with log1pf above the exact ln(1 + e^-t) of the f32 Min*-approx / A-Min* rules (reference src/decoder/arithmetic.rs:510,
+// :965-966) in their opt-in bit-exact mode.  kLibmExactExp2fTab[i] = bits(2^(i/32)) - (i << 47).
+LME_TAB64 kLibmExactExp2fTab[32] = {
+0x3ff0000000000000ull,
+0x3fefd9b0d3158574ull,
+0x3fefb5586cf9890full,
+0x3fef9301d0125b51ull,
+0x3fef72b83c7d517bull,
+0x3fef54873168b9aaull,
+0x3fef387a6e756238ull,
+0x3fef1e9df51fdee1ull,
+0x3fef06fe0a31b715ull,
+0x3feef1a7373aa9cbull,
+0x3feedea64c123422ull,
+0x3feece086061892dull,
+0x3feebfdad5362a27ull,
+0x3feeb42b569d4f82ull,
+0x3feeab07dd485429ull,
+0x3feea47eb03a5585ull,
+0x3feea09e667f3bcdull,
+0x3fee9f75e8ec5f74ull,
+0x3feea11473eb0187ull,
+0x3feea589994cce13ull,
+0x3feeace5422aa0dbull,
+0x3feeb737b0cdc5e5ull,
+0x3feec49182a3f090ull,
+0x3feed503b23e255dull,
+0x3feee89f995ad3adull,
+0x3feeff76f2fb5e47ull,
+0x3fef199bdd85529cull,
+0x3fef3720dcef9069ull,
+0x3fef5818dcfba487ull,
+0x3fef7c97337b9b5full,
+0x3fefa4afa2a490daull,
+0x3fefd0765b6e4540ull};
+
+LME_FN float libm_exact_expf(float x) {
+    const double InvLn2N = 0x1.71547652b82fep+5, Shift = 0x1.8p+52, C0 = 0x1.c6af84b912394p-20, C1 = 0x1.ebfce50fac4f3p-13,
+                 C2 = 0x1.62e42ff0c52d6p-6;
+    const uint32_t ux = LME_F2U(x), abstop = (ux >> 20) & 0x7ff;
+    if (abstop >= (0x42b00000u >> 20)) {             // |x| >= 88 or NaN
+        if (ux == 0xff800000u) return 0.0f;
+        if (abstop >= (0x7f800000u >> 20)) return LME_FADD(x, x);
+        if (x > 0x1.62e42ep6f) return LME_INF;       // overflow
+        if (x < -0x1.9fe368p6f) return 0.0f;         // underflow
+    }
+    const double xd = (double)x;
+    double z = LME_DMUL(InvLn2N, xd);
+    double kd = LME_DADD(z, Shift);
+    const uint64_t ki = LME_D2U(kd);
+    kd = LME_DADD(kd, -Shift);
+    // x86-64 glibc dispatches expf to its FMA build on every CPU that has FMA (sysdeps/x86_64/fpu/multiarch/e_expf.c); there the
+    // compiler contracts r = InvLn2N x - kd and the three polynomial steps into fused multiply-adds, and two floats out of
+    // 2.2 billion round differently without the first of them (x = 0x1.04845ep+5 and -0x1.f8cbb2p+5)
+    const double r = LME_DFMA(InvLn2N, xd, -kd);
+    uint64_t t = LME_LOAD(&kLibmExactExp2fTab[ki & 31]);
+    t += ki << 47;
+    const double s = LME_U2D(t);
+    z = LME_DFMA(C0, r, C1);
+    const double r2 = LME_DMUL(r, r);
+    double y = LME_DFMA(C2, r, 1.0);
+    y = LME_DFMA(z, r2, y);
+    y = LME_DMUL(y, s);
+    return LME_D2F(y);
 }

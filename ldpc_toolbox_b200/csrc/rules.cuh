@@ -18,7 +18,13 @@ namespace ldpc {
 
 constexpr int kRuleMaxD = 32;        // largest check degree handled by the generic kernels
 
-enum RuleId { kPhi = 0, kTanh = 1, kMinstarapprox = 2, kAminstar = 3 };
+// kMinstarapproxExact / kAminstarExact: the same rules with ln(1 + e^-t) evaluated by bit-exact ports of glibc's expf and
+// log1pf (libm_exact.h) instead of the fast polynomial — the opt-in bit-exact mode of the f32 decoders (LDPC_B200_EXACT_LIBM=1);
+// for f64 they are aliases of the plain rules.
+enum RuleId { kPhi = 0, kTanh = 1, kMinstarapprox = 2, kAminstar = 3, kMinstarapproxExact = 4, kAminstarExact = 5 };
+__host__ __device__ constexpr bool rule_is_minstar(int r) { return r == kMinstarapprox || r == kMinstarapproxExact; }
+__host__ __device__ constexpr bool rule_is_aminstar(int r) { return r == kAminstar || r == kAminstarExact; }
+__host__ __device__ constexpr bool rule_is_exact(int r) { return r == kMinstarapproxExact || r == kAminstarExact; }
 
 
 #include "libm_exact.h"
@@ -70,6 +76,9 @@ template <> struct FMath<float> {
         return p * e;
 #endif
     }
+    // the reference's own evaluation, (-t).exp().ln_1p() in f32, on bit-exact ports of the libm functions it calls
+    // (a real call: inlining ~90 instructions into every step of the unrolled folds took the build from 9 to 25 minutes)
+    static __device__ __noinline__ float softplus_exact(float t) { return libm_exact_log1pf(libm_exact_expf(-t)); }
 };
 template <> struct FMath<double> {
     static __device__ __forceinline__ double tanh_(double x) { return tanh(x); }
@@ -80,6 +89,7 @@ template <> struct FMath<double> {
     static __device__ __forceinline__ double log1p_(double x) { return log1p(x); }
     static __device__ __forceinline__ double atanh_(double x) { return atanh(x); }
     static __device__ __forceinline__ double softplus_neg(double t) { return log1p(exp(-t)); }
+    static __device__ __forceinline__ double softplus_exact(double t) { return log1p(exp(-t)); }
     static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
     static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
     static __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
@@ -124,9 +134,10 @@ __device__ __forceinline__ void check_rule_float(const F* x, int d_rt, F* out, F
                 if (i != j) prod *= scratch[i];
             out[j] = F(2) * M::atanh_(prod);
         }
-    } else if (RULE == kMinstarapprox) {
+    } else if (rule_is_minstar(RULE)) {
         auto g = [](F a, F acc) {                              // arithmetic.rs:510
-            return M::max_(M::min_(a, acc) - M::softplus_neg(M::abs_(a - acc)), F(0));
+            const F sp = rule_is_exact(RULE) ? M::softplus_exact(M::abs_(a - acc)) : M::softplus_neg(M::abs_(a - acc));
+            return M::max_(M::min_(a, acc) - sp, F(0));
         };
         // shared prefix P_j = fold(|x_0| .. |x_{j-1}|); the remaining terms are folded per output
         F P = F(0);
@@ -147,6 +158,7 @@ __device__ __forceinline__ void check_rule_float(const F* x, int d_rt, F* out, F
         }
     } else {                                                   // A-Min*
         auto h = [](F a, F b) {                                // arithmetic.rs:965-966
+            if (rule_is_exact(RULE)) return M::min_(a, b) - M::softplus_exact(M::abs_(a - b)) + M::softplus_exact(a + b);
             return M::min_(a, b) - M::softplus_neg(M::abs_(a - b)) + M::softplus_neg(a + b);
         };
         int arg = 0;

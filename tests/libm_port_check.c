@@ -32,7 +32,23 @@ int main(int argc, char** argv) {
         bad_atanh += lme_f2u(atanhf(-x)) != lme_f2u(libm_exact_atanhf(-x));
         ++n_atanh;
     }
+    long bad_exp = 0, n_exp = 0, bad_l1p = 0, n_l1p = 0;
+    const uint32_t e_hi = lme_f2u(104.0f), p_hi = lme_f2u(2.0f);
+#pragma omp parallel for reduction(+ : bad_exp, n_exp) schedule(static)
+    for (uint32_t u = 0; u <= e_hi; u += stride) {                 /* exp(-t), t in [0, 104]; and exp(+t) up to overflow */
+        const float x = lme_u2f(u);
+        bad_exp += lme_f2u(expf(-x)) != lme_f2u(libm_exact_expf(-x));
+        bad_exp += lme_f2u(expf(x)) != lme_f2u(libm_exact_expf(x));
+        ++n_exp;
+    }
+#pragma omp parallel for reduction(+ : bad_l1p, n_l1p) schedule(static)
+    for (uint32_t u = 0; u <= p_hi; u += stride) {                 /* log1p(e), e = exp(-t) in [0, 1] (checked up to 2) */
+        const float x = lme_u2f(u);
+        bad_l1p += lme_f2u(log1pf(x)) != lme_f2u(libm_exact_log1pf(x));
+        ++n_l1p;
+    }
+    printf("{\"expf_checked\": %ld, \"expf_mismatches\": %ld, \"log1pf_checked\": %ld, \"log1pf_mismatches\": %ld}\n", n_exp, bad_exp, n_l1p, bad_l1p);
     printf("{\"atanhf_checked\": %ld, \"atanhf_mismatches\": %ld}\n", n_atanh, bad_atanh);
     printf("{\"tanhf_checked\": %ld, \"tanhf_mismatches\": %ld, \"logf_checked\": %ld, \"logf_mismatches\": %ld}\n", n_tanh, bad_tanh, n_log, bad_log);
-    return bad_tanh || bad_log || bad_atanh;
+    return bad_tanh || bad_log || bad_atanh || bad_exp || bad_l1p;
 }

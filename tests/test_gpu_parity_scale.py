@@ -103,3 +103,16 @@ def test_float_words_at_scale(oracle, code, impl, ebn0, max_iter, frames, allowe
     assert differs.sum() <= allowed, f"{impl}: {int(differs.sum())} of {frames} words differ"
     assert (its != rits).sum() <= 8 * allowed, f"{impl}: {int((its != rits).sum())} iteration counts differ"
     assert (rits > 0).sum() > frames // 2
+
+
+@pytest.mark.parametrize("code,impl,ebn0,max_iter,frames", [
+    ("ar4ja:1/2:1024", "Minstarapproxf32", 1.6, 50, 8192),
+    ("ar4ja:1/2:1024", "Aminstarf32", 1.6, 50, 8192),
+    ("nr5g:2:96", "HLMinstarapproxf32", 1.0, 30, 8192),
+    ("nr5g:2:96", "HLAminstarf32", 1.0, 30, 8192),
+])
+def test_f32_minstar_exact_libm_mode_is_bit_exact(oracle, code, impl, ebn0, max_iter, frames, monkeypatch):
+    """LDPC_B200_EXACT_LIBM=1: ln(1 + e^-t) through the bit-exact ports of glibc's expf / log1pf (libm_exact.h) instead
+    of the fast polynomial — every word and iteration count must then equal the checker's."""
+    monkeypatch.setenv("LDPC_B200_EXACT_LIBM", "1")
+    test_float_words_at_scale(oracle, code, impl, ebn0, max_iter, frames, 0)
