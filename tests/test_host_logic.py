@@ -151,6 +151,57 @@ def test_ber_driver_stop_rule_and_sharding():
     assert s.bch.frame_errors == 0 and s.ldpc.frame_errors == 20 and s.num_frames == 140
 
 
+class FakeAsyncEngine(FakeEngine):
+    """FakeEngine with the asynchronous submit / wait pair of the GPU engine (two tickets in flight at most)."""
+
+    def __init__(self):
+        super().__init__()
+        self.pending = {}
+        self.next = 0
+        self.max_in_flight = 0
+
+    def submit(self, ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors):
+        assert len(self.pending) < 2, "a third submit without a wait"
+        c = np.zeros(9, dtype=np.uint64)
+        self.run(ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors, c)
+        t, self.next = self.next, self.next + 1
+        self.pending[t] = c
+        self.max_in_flight = max(self.max_in_flight, len(self.pending))
+        return t
+
+    def wait(self, ticket, counters=None):
+        c = self.pending.pop(ticket)
+        if counters is None:
+            return c
+        counters += c
+        return counters
+
+
+def test_ber_driver_pipelined_rounds():
+    """Two rounds in flight per engine (ber.py BerTest with submit / wait engines): rounds are collected in order, the
+    stop rule is applied to completed rounds, rounds already submitted when it fires are still counted (the stated
+    overshoot bound), and --max-frames never submits more than asked."""
+    from ldpc_toolbox_b200.ber import BerTest
+    engines = [FakeAsyncEngine(), FakeAsyncEngine()]
+    t = BerTest(engines, k=10, ebn0s_db=[1.0], max_iterations=5, max_frame_errors=20, batch=50)
+    assert t.pipeline_depth == 2 and t.overshoot_bound() == 100
+    s = t.run()[0]
+    assert all(e.max_in_flight == 2 and not e.pending for e in engines)
+    blocking = BerTest([FakeEngine(), FakeEngine()], k=10, ebn0s_db=[1.0], max_iterations=5, max_frame_errors=20, batch=50).run()[0]
+    # the pipelined driver stops exactly one round (100 frames) after the blocking one, and counts that round
+    assert s.num_frames == blocking.num_frames + 100
+    seen = sorted(c for e in engines for c in e.calls)
+    for (a, n), (b, _) in zip(seen, seen[1:]):
+        assert a + n == b                                  # disjoint, gap-free global frame ranges
+    assert seen[0][0] == 0 and seen[-1][0] + seen[-1][1] == s.num_frames
+    # max_frames: whole rounds up to the limit, nothing beyond
+    e2 = [FakeAsyncEngine()]
+    s2 = BerTest(e2, k=10, ebn0s_db=[1.0], max_iterations=5, max_frame_errors=10**9, batch=64, max_frames=200).run()[0]
+    assert s2.num_frames == 256 and len(e2[0].calls) == 4
+    # a mixed list (one engine without submit) falls back to blocking rounds
+    assert BerTest([FakeAsyncEngine(), FakeEngine()], k=10, ebn0s_db=[1.0], batch=8).pipeline_depth == 1
+
+
 def _gloo_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
@@ -209,6 +260,41 @@ def _gloo_worker_max_time(rank, world, port, q):
     st = t.run()
     q.put((rank, [s.num_frames for s in st], [s.ldpc.frame_errors for s in st]))
     dist.destroy_process_group()
+
+
+def _gloo_worker_async(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from ldpc_toolbox_b200.ber import BerTest
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+    def allreduce(c):
+        t = torch.from_numpy(c.astype(np.int64))
+        dist.all_reduce(t)
+        return t.numpy().astype(np.uint64)
+
+    t = BerTest([FakeAsyncEngine()], k=10, ebn0s_db=[1.0, 2.0], max_iterations=5, max_frame_errors=30, batch=64, rank=rank, world=world,
+                allreduce=allreduce)
+    st = t.run()
+    q.put((rank, [s.num_frames for s in st], [s.ldpc.frame_errors for s in st], [s.total_iterations for s in st]))
+    dist.destroy_process_group()
+
+
+def test_ber_driver_world_size_2_gloo_pipelined():
+    """Two ranks, two rounds in flight each (asynchronous engines), counters all-reduced per collected round: both ranks
+    must stop on the same round with the same global counts, one round after the blocking driver would."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker_async, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    assert res[0][1:] == res[1][1:]
+    from ldpc_toolbox_b200.ber import BerTest
+    single = BerTest([FakeEngine(), FakeEngine()], k=10, ebn0s_db=[1.0, 2.0], max_iterations=5, max_frame_errors=30, batch=64).run()
+    assert res[0][1] == [s.num_frames + 128 for s in single]
 
 
 def test_ber_driver_world_size_2_gloo_time_limited():
