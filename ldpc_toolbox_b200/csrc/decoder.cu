@@ -188,8 +188,8 @@ public:
     // Asynchronous host-buffer decode.  The batch is cut into chunks that flow through a three-stage
     // pipeline — H2D copy (copy engine) -> ingest + BP + emit -> D2H copy — over two staging slots.  The int8
     // flooding decoder on big batches uses chunks of HALF a GPU-filling launch on two compute streams with
-    // their own workspaces, so two launches are co-resident (one CTA per SM each): the exposed prologue is
-    // the copy of half a launch, a finishing launch is replaced while the other keeps the SMs busy, and
+    // their own workspaces (a half-launch still fills the GPU: one 2-CTA cluster per tile): the exposed
+    // prologue is the copy of half a launch, the other lane's kernels are already queued when a launch ends, and
     // consecutive submit_batch calls keep the pipeline full.  Nothing here blocks the host when the caller's
     // buffers are pinned; wait(ticket) does.
     int64_t submit_batch(const void* llrs, bool is_f64, size_t llrs_len, size_t nframes, uint32_t max_iterations,
