@@ -2,6 +2,7 @@
 // Replaces reference src/c_api.rs, src/c_api/decoder.rs and src/c_api/encoder.rs.
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <fstream>
 #include <sstream>
 
@@ -18,6 +19,16 @@ float average_decode_ms(LdpcDecoder* d, int64_t* launches);
 using namespace ldpc;
 
 namespace {
+
+// No C++ exception may cross the C boundary (std::bad_alloc on an absurd alist header, std::length_error ...):
+// the call fails with its error value and ldpc_toolbox_last_error() says why.
+template <class R, class F>
+R guarded(R on_error, F&& f) noexcept {
+    try { return f(); }
+    catch (const std::exception& e) { set_last_error(std::string("internal error: ") + e.what()); }
+    catch (...) { set_last_error("internal error"); }
+    return on_error;
+}
 
 struct DecoderHandle {                       // reference c_api/decoder.rs:19-23
     std::unique_ptr<LdpcDecoder> decoder;
@@ -48,74 +59,86 @@ bool make_puncturer(const char* puncturing, std::unique_ptr<Puncturer>* p) {
 }
 
 void* decoder_new(const std::string& alist, const char* implementation, const char* puncturing, int device, int max_tiles) {
-    Graph g;
-    std::string err;
-    if (!Graph::from_alist(alist, &g, &err)) { set_last_error(err); return nullptr; }
-    DecoderImplementation impl;
-    if (!DecoderImplementation::parse(implementation, &impl)) { set_last_error("invalid decoder implementation"); return nullptr; }
-    std::unique_ptr<Puncturer> p;
-    if (!make_puncturer(puncturing, &p)) return nullptr;
-    DecoderOptions opt;
-    opt.device = device;
-    opt.max_tiles = max_tiles;
-    auto dec = build_decoder(impl, g, p.get(), opt);
-    if (!dec) return nullptr;
-    auto* h = new DecoderHandle();
-    h->decoder = std::move(dec);
-    return h;
+    return guarded<void*>(nullptr, [&]() -> void* {
+        Graph g;
+        std::string err;
+        if (!Graph::from_alist(alist, &g, &err)) { set_last_error(err); return nullptr; }
+        DecoderImplementation impl;
+        if (!DecoderImplementation::parse(implementation, &impl)) { set_last_error("invalid decoder implementation"); return nullptr; }
+        std::unique_ptr<Puncturer> p;
+        if (!make_puncturer(puncturing, &p)) return nullptr;
+        DecoderOptions opt;
+        opt.device = device;
+        opt.max_tiles = max_tiles;
+        auto dec = build_decoder(impl, g, p.get(), opt);
+        if (!dec) return nullptr;
+        auto* h = new DecoderHandle();
+        h->decoder = std::move(dec);
+        return h;
+    });
 }
 
 void* encoder_new(const std::string& alist, const char* puncturing) {
-    Graph g;
-    std::string err;
-    if (!Graph::from_alist(alist, &g, &err)) { set_last_error(err); return nullptr; }
-    std::unique_ptr<Puncturer> p;
-    if (!make_puncturer(puncturing, &p)) return nullptr;
-    auto h = std::make_unique<EncoderHandle>();
-    if (!EncoderPlan::from_graph(g, &h->plan, &err)) { set_last_error(err); return nullptr; }
-    if (p) {
-        h->punctured = true;
-        // the reference only fails at encode time (puncture() -> unwrap); remember an empty map
-        if (!p->puncture_map((size_t)g.n, &h->kept)) h->kept.assign(1, -1);
-    }
-    h->msg.resize((size_t)h->plan.k);
-    h->cw.resize((size_t)h->plan.n);
-    return h.release();
+    return guarded<void*>(nullptr, [&]() -> void* {
+        Graph g;
+        std::string err;
+        if (!Graph::from_alist(alist, &g, &err)) { set_last_error(err); return nullptr; }
+        std::unique_ptr<Puncturer> p;
+        if (!make_puncturer(puncturing, &p)) return nullptr;
+        auto h = std::make_unique<EncoderHandle>();
+        if (!EncoderPlan::from_graph(g, &h->plan, &err)) { set_last_error(err); return nullptr; }
+        if (p) {
+            h->punctured = true;
+            // the reference only fails at encode time (puncture() -> unwrap); remember an empty map
+            if (!p->puncture_map((size_t)g.n, &h->kept)) h->kept.assign(1, -1);
+        }
+        h->msg.resize((size_t)h->plan.k);
+        h->cw.resize((size_t)h->plan.n);
+        return h.release();
+    });
 }
 
 template <class T>
 int32_t decode_single(void* decoder, uint8_t* output, size_t output_len, const T* llrs, size_t llrs_len, uint32_t max_it) {
-    if (!decoder || (!output && output_len) || !llrs) return -2;
-    auto* h = static_cast<DecoderHandle*>(decoder);
-    int32_t it = -2;
-    if (!h->decoder->decode_batch(llrs, sizeof(T) == 8, llrs_len, 1, max_it, output, output_len, output_len, &it)) return -2;
-    return it;
+    return guarded<int32_t>(-2, [&]() -> int32_t {
+        if (!decoder || (!output && output_len) || !llrs) return -2;
+        auto* h = static_cast<DecoderHandle*>(decoder);
+        int32_t it = -2;
+        if (!h->decoder->decode_batch(llrs, sizeof(T) == 8, llrs_len, 1, max_it, output, output_len, output_len, &it)) return -2;
+        return it;
+    });
 }
 
 template <class T>
 int32_t decode_batch(void* decoder, uint8_t* output, size_t output_len, size_t output_stride, const T* llrs, size_t llrs_len,
                      size_t nframes, uint32_t max_it, int32_t* iterations) {
-    if (!decoder || !iterations || !llrs || (!output && output_len)) return -2;
-    auto* h = static_cast<DecoderHandle*>(decoder);
-    return h->decoder->decode_batch(llrs, sizeof(T) == 8, llrs_len, nframes, max_it, output, output_len, output_stride, iterations) ? 0 : -2;
+    return guarded<int32_t>(-2, [&]() -> int32_t {
+        if (!decoder || !iterations || !llrs || (!output && output_len)) return -2;
+        auto* h = static_cast<DecoderHandle*>(decoder);
+        return h->decoder->decode_batch(llrs, sizeof(T) == 8, llrs_len, nframes, max_it, output, output_len, output_stride, iterations) ? 0 : -2;
+    });
 }
 
 template <class T>
 int64_t submit_batch(void* decoder, uint8_t* output, size_t output_len, size_t output_stride, const T* llrs, size_t llrs_len,
                      size_t nframes, uint32_t max_it, int32_t* iterations) {
-    if (!decoder || !iterations || !llrs || (!output && output_len)) return -2;
-    auto* h = static_cast<DecoderHandle*>(decoder);
-    const int64_t t = h->decoder->submit_batch(llrs, sizeof(T) == 8, llrs_len, nframes, max_it, output, output_len, output_stride, iterations);
-    return t >= 0 ? t : -2;
+    return guarded<int64_t>(-2, [&]() -> int64_t {
+        if (!decoder || !iterations || !llrs || (!output && output_len)) return -2;
+        auto* h = static_cast<DecoderHandle*>(decoder);
+        const int64_t t = h->decoder->submit_batch(llrs, sizeof(T) == 8, llrs_len, nframes, max_it, output, output_len, output_stride, iterations);
+        return t >= 0 ? t : -2;
+    });
 }
 
 template <class T>
 int32_t decode_batch_device(void* decoder, uint8_t* d_output, size_t output_len, size_t output_stride, const T* d_llrs,
                             size_t llrs_len, size_t nframes, uint32_t max_it, int32_t* d_iterations, void* stream) {
-    if (!decoder || !d_iterations || !d_llrs || (!d_output && output_len)) return -2;
-    auto* h = static_cast<DecoderHandle*>(decoder);
-    return h->decoder->decode_batch_device(d_llrs, sizeof(T) == 8, llrs_len, nframes, max_it, d_output, output_len, output_stride,
-                                           d_iterations, static_cast<cudaStream_t>(stream)) ? 0 : -2;
+    return guarded<int32_t>(-2, [&]() -> int32_t {
+        if (!decoder || !d_iterations || !d_llrs || (!d_output && output_len)) return -2;
+        auto* h = static_cast<DecoderHandle*>(decoder);
+        return h->decoder->decode_batch_device(d_llrs, sizeof(T) == 8, llrs_len, nframes, max_it, d_output, output_len, output_stride,
+                                               d_iterations, static_cast<cudaStream_t>(stream)) ? 0 : -2;
+    });
 }
 
 }  // namespace
@@ -123,26 +146,32 @@ int32_t decode_batch_device(void* decoder, uint8_t* d_output, size_t output_len,
 extern "C" {
 
 void* ldpc_toolbox_decoder_ctor(const char* alist_file_path, const char* implementation, const char* puncturing) {
-    if (!alist_file_path || !implementation || !puncturing) return nullptr;
-    std::string s;
-    if (!slurp(alist_file_path, &s)) return nullptr;
-    return decoder_new(s, implementation, puncturing, -1, 0);
+    return guarded<void*>(nullptr, [&]() -> void* {
+        if (!alist_file_path || !implementation || !puncturing) return nullptr;
+        std::string s;
+        if (!slurp(alist_file_path, &s)) return nullptr;
+        return decoder_new(s, implementation, puncturing, -1, 0);
+    });
 }
 
 void* ldpc_toolbox_decoder_ctor_alist_string(const char* alist, const char* implementation, const char* puncturing) {
-    if (!alist || !implementation || !puncturing) return nullptr;
-    return decoder_new(alist, implementation, puncturing, -1, 0);
+    return guarded<void*>(nullptr, [&]() -> void* {
+        if (!alist || !implementation || !puncturing) return nullptr;
+        return decoder_new(alist, implementation, puncturing, -1, 0);
+    });
 }
 
 void* ldpc_toolbox_decoder_ctor_ex(const char* alist, int alist_is_path, const char* implementation, const char* puncturing,
                                    int device, int max_tiles) {
-    if (!alist || !implementation || !puncturing) return nullptr;
-    if (alist_is_path) {
-        std::string s;
-        if (!slurp(alist, &s)) return nullptr;
-        return decoder_new(s, implementation, puncturing, device, max_tiles);
-    }
-    return decoder_new(alist, implementation, puncturing, device, max_tiles);
+    return guarded<void*>(nullptr, [&]() -> void* {
+        if (!alist || !implementation || !puncturing) return nullptr;
+        if (alist_is_path) {
+            std::string s;
+            if (!slurp(alist, &s)) return nullptr;
+            return decoder_new(s, implementation, puncturing, device, max_tiles);
+        }
+        return decoder_new(alist, implementation, puncturing, device, max_tiles);
+    });
 }
 
 void ldpc_toolbox_decoder_dtor(void* decoder) { delete static_cast<DecoderHandle*>(decoder); }
@@ -184,22 +213,28 @@ int64_t ldpc_toolbox_decoder_submit_batch_f64(void* decoder, uint8_t* output, si
 int32_t ldpc_toolbox_decoder_decode_batch_posteriors_f32(void* decoder, uint8_t* output, size_t output_len, size_t output_stride,
                                                          const float* llrs, size_t llrs_len, size_t nframes, uint32_t max_iterations,
                                                          int32_t* iterations, double* posteriors) {
-    if (!decoder || !iterations || !llrs || !posteriors || (!output && output_len)) return -2;
-    return static_cast<DecoderHandle*>(decoder)->decoder->decode_batch_posteriors(llrs, false, llrs_len, nframes, max_iterations, output,
-                                                                                  output_len, output_stride, iterations, posteriors) ? 0 : -2;
+    return guarded<int32_t>(-2, [&]() -> int32_t {
+        if (!decoder || !iterations || !llrs || !posteriors || (!output && output_len)) return -2;
+        return static_cast<DecoderHandle*>(decoder)->decoder->decode_batch_posteriors(llrs, false, llrs_len, nframes, max_iterations, output,
+                                                                                      output_len, output_stride, iterations, posteriors) ? 0 : -2;
+    });
 }
 
 int32_t ldpc_toolbox_decoder_decode_batch_posteriors_f64(void* decoder, uint8_t* output, size_t output_len, size_t output_stride,
                                                          const double* llrs, size_t llrs_len, size_t nframes, uint32_t max_iterations,
                                                          int32_t* iterations, double* posteriors) {
-    if (!decoder || !iterations || !llrs || !posteriors || (!output && output_len)) return -2;
-    return static_cast<DecoderHandle*>(decoder)->decoder->decode_batch_posteriors(llrs, true, llrs_len, nframes, max_iterations, output,
-                                                                                  output_len, output_stride, iterations, posteriors) ? 0 : -2;
+    return guarded<int32_t>(-2, [&]() -> int32_t {
+        if (!decoder || !iterations || !llrs || !posteriors || (!output && output_len)) return -2;
+        return static_cast<DecoderHandle*>(decoder)->decoder->decode_batch_posteriors(llrs, true, llrs_len, nframes, max_iterations, output,
+                                                                                      output_len, output_stride, iterations, posteriors) ? 0 : -2;
+    });
 }
 
 int32_t ldpc_toolbox_decoder_wait(void* decoder, int64_t ticket) {
-    if (!decoder || ticket < 0) return -2;
-    return static_cast<DecoderHandle*>(decoder)->decoder->wait(ticket) ? 0 : -2;
+    return guarded<int32_t>(-2, [&]() -> int32_t {
+        if (!decoder || ticket < 0) return -2;
+        return static_cast<DecoderHandle*>(decoder)->decoder->wait(ticket) ? 0 : -2;
+    });
 }
 
 int32_t ldpc_toolbox_decoder_decode_batch_device_f32(void* decoder, uint8_t* d_output, size_t output_len, size_t output_stride,
@@ -237,15 +272,19 @@ float ldpc_toolbox_decoder_average_decode_ms(void* d, int64_t* launches) {
 }
 
 void* ldpc_toolbox_encoder_ctor(const char* alist_file_path, const char* puncturing) {
-    if (!alist_file_path || !puncturing) return nullptr;
-    std::string s;
-    if (!slurp(alist_file_path, &s)) return nullptr;
-    return encoder_new(s, puncturing);
+    return guarded<void*>(nullptr, [&]() -> void* {
+        if (!alist_file_path || !puncturing) return nullptr;
+        std::string s;
+        if (!slurp(alist_file_path, &s)) return nullptr;
+        return encoder_new(s, puncturing);
+    });
 }
 
 void* ldpc_toolbox_encoder_ctor_alist_string(const char* alist, const char* puncturing) {
-    if (!alist || !puncturing) return nullptr;
-    return encoder_new(alist, puncturing);
+    return guarded<void*>(nullptr, [&]() -> void* {
+        if (!alist || !puncturing) return nullptr;
+        return encoder_new(alist, puncturing);
+    });
 }
 
 void ldpc_toolbox_encoder_dtor(void* encoder) { delete static_cast<EncoderHandle*>(encoder); }
@@ -268,54 +307,66 @@ void ldpc_toolbox_encoder_encode(void* encoder, uint8_t* output, size_t output_l
 
 void* ldpc_toolbox_ber_ctor(const char* alist, int alist_is_path, const char* implementation, const char* puncturing, int device,
                             int max_tiles) {
-    if (!alist || !implementation || !puncturing) return nullptr;
-    std::string text;
-    if (alist_is_path) { if (!slurp(alist, &text)) return nullptr; } else text = alist;
-    Graph g;
-    std::string err;
-    if (!Graph::from_alist(text, &g, &err)) { set_last_error(err); return nullptr; }
-    DecoderImplementation impl;
-    if (!DecoderImplementation::parse(implementation, &impl)) { set_last_error("invalid decoder implementation"); return nullptr; }
-    std::unique_ptr<Puncturer> p;
-    if (!make_puncturer(puncturing, &p)) return nullptr;
-    DecoderOptions opt;
-    opt.device = device;
-    opt.max_tiles = max_tiles;
-    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { set_last_error("cudaSetDevice failed"); return nullptr; }
-    return BerEngine::create(g, impl, p.get(), opt).release();
+    return guarded<void*>(nullptr, [&]() -> void* {
+        if (!alist || !implementation || !puncturing) return nullptr;
+        std::string text;
+        if (alist_is_path) { if (!slurp(alist, &text)) return nullptr; } else text = alist;
+        Graph g;
+        std::string err;
+        if (!Graph::from_alist(text, &g, &err)) { set_last_error(err); return nullptr; }
+        DecoderImplementation impl;
+        if (!DecoderImplementation::parse(implementation, &impl)) { set_last_error("invalid decoder implementation"); return nullptr; }
+        std::unique_ptr<Puncturer> p;
+        if (!make_puncturer(puncturing, &p)) return nullptr;
+        DecoderOptions opt;
+        opt.device = device;
+        opt.max_tiles = max_tiles;
+        if (device >= 0 && cudaSetDevice(device) != cudaSuccess) { set_last_error("cudaSetDevice failed"); return nullptr; }
+        return BerEngine::create(g, impl, p.get(), opt).release();
+    });
 }
 
 void ldpc_toolbox_ber_dtor(void* ber) { delete static_cast<BerEngine*>(ber); }
 
 int32_t ldpc_toolbox_ber_set_modulation(void* ber, const char* modulation, int32_t interleaving_columns) {
-    if (!ber || !modulation) return -2;
-    return static_cast<BerEngine*>(ber)->set_modulation(modulation, interleaving_columns) ? 0 : -2;
+    return guarded<int32_t>(-2, [&]() -> int32_t {
+        if (!ber || !modulation) return -2;
+        return static_cast<BerEngine*>(ber)->set_modulation(modulation, interleaving_columns) ? 0 : -2;
+    });
 }
 
 int32_t ldpc_toolbox_ber_run(void* ber, float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes, uint64_t seed,
                              uint64_t bch_max_errors, uint64_t* counters) {
-    if (!ber || !counters) return -2;
-    return static_cast<BerEngine*>(ber)->run(ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors, counters) ? 0 : -2;
+    return guarded<int32_t>(-2, [&]() -> int32_t {
+        if (!ber || !counters) return -2;
+        return static_cast<BerEngine*>(ber)->run(ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors, counters) ? 0 : -2;
+    });
 }
 
 int32_t ldpc_toolbox_ber_run_dump(void* ber, float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes,
                                   uint64_t seed, uint64_t bch_max_errors, uint64_t* counters, float* llrs, uint8_t* decoded,
                                   int32_t* iterations, uint32_t* messages) {
-    if (!ber || !counters) return -2;
-    return static_cast<BerEngine*>(ber)->run(ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors, counters, llrs,
-                                             decoded, iterations, messages) ? 0 : -2;
+    return guarded<int32_t>(-2, [&]() -> int32_t {
+        if (!ber || !counters) return -2;
+        return static_cast<BerEngine*>(ber)->run(ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors, counters, llrs,
+                                                 decoded, iterations, messages) ? 0 : -2;
+    });
 }
 
 int64_t ldpc_toolbox_ber_submit(void* ber, float ebn0_db, uint32_t max_iterations, uint64_t first_frame, uint64_t nframes, uint64_t seed,
                                 uint64_t bch_max_errors) {
-    if (!ber) return -2;
-    const int64_t t = static_cast<BerEngine*>(ber)->submit(ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors);
-    return t >= 0 ? t : -2;
+    return guarded<int64_t>(-2, [&]() -> int64_t {
+        if (!ber) return -2;
+        const int64_t t = static_cast<BerEngine*>(ber)->submit(ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors);
+        return t >= 0 ? t : -2;
+    });
 }
 
 int32_t ldpc_toolbox_ber_wait(void* ber, int64_t ticket, uint64_t* counters) {
-    if (!ber || !counters) return -2;
-    return static_cast<BerEngine*>(ber)->wait(ticket, counters) ? 0 : -2;
+    return guarded<int32_t>(-2, [&]() -> int32_t {
+        if (!ber || !counters) return -2;
+        return static_cast<BerEngine*>(ber)->wait(ticket, counters) ? 0 : -2;
+    });
 }
 
 void ldpc_toolbox_ber_dims(void* ber, uint64_t* what3) {

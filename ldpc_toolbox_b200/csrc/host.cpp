@@ -78,7 +78,9 @@ bool Graph::from_alist(const std::string& text, Graph* out, std::string* err) {
     const int ncols = (int)dims[0], nrows = (int)dims[1];
     for (int i = 0; i < 3; ++i) cur.next(&b, &e);   // max weights, column weights, row weights: ignored
 
-    std::vector<std::vector<int>> rows((size_t)nrows);
+    // every column needs a line of its own, so a header that promises more columns than the text has bytes is
+    // refused before anything is sized by it
+    if ((size_t)ncols > text.size()) return fail("alist does not contain expected number of lines");
     std::vector<int> col_ptr((size_t)ncols + 1, 0), col_row;
     for (int c = 0; c < ncols; ++c) {
         if (!cur.next(&b, &e)) return fail("alist does not contain expected number of lines");
@@ -95,35 +97,36 @@ bool Graph::from_alist(const std::string& text, Graph* out, std::string* err) {
         });
         if (!range_ok) return fail("row index out of range");
         if (!ok) return fail("row value is not a number");
+        if (col_row.size() > 0x7fffffffULL) return fail("matrix too large");
         col_ptr[(size_t)c + 1] = (int)col_row.size();
-        for (size_t i = start; i < col_row.size(); ++i) rows[(size_t)col_row[i]].push_back(c);
     }
 
+    // rows by counting: columns are visited in increasing order, so every row's entries come out sorted by
+    // column, and the slot an entry lands in is its edge index
     Graph g;
     g.n = ncols; g.m = nrows; g.E = (int)col_row.size();
     g.row_ptr.assign((size_t)nrows + 1, 0);
-    for (int r = 0; r < nrows; ++r) g.row_ptr[(size_t)r + 1] = g.row_ptr[(size_t)r] + (int)rows[(size_t)r].size();
-    g.col_idx.reserve((size_t)g.E);
+    for (int r : col_row) ++g.row_ptr[(size_t)r + 1];
     g.max_row_deg = 0; g.min_row_deg = nrows ? 1 << 30 : 0;
     for (int r = 0; r < nrows; ++r) {
-        for (int c : rows[(size_t)r]) g.col_idx.push_back(c);
-        int d = (int)rows[(size_t)r].size();
+        const int d = g.row_ptr[(size_t)r + 1];
         g.max_row_deg = std::max(g.max_row_deg, d);
         g.min_row_deg = std::min(g.min_row_deg, d);
+        g.row_ptr[(size_t)r + 1] += g.row_ptr[(size_t)r];
+    }
+    g.col_idx.resize((size_t)g.E);
+    g.col_edge.resize((size_t)g.E);
+    std::vector<int> fill(g.row_ptr.begin(), g.row_ptr.end() - 1);
+    for (int c = 0; c < ncols; ++c) {
+        for (int p = col_ptr[(size_t)c]; p < col_ptr[(size_t)c + 1]; ++p) {
+            const int slot = fill[(size_t)col_row[(size_t)p]]++;
+            g.col_idx[(size_t)slot] = c;
+            g.col_edge[(size_t)p] = slot;
+        }
+        g.max_col_deg = std::max(g.max_col_deg, col_ptr[(size_t)c + 1] - col_ptr[(size_t)c]);
     }
     g.col_ptr = std::move(col_ptr);
     g.col_row = std::move(col_row);
-    g.col_edge.resize((size_t)g.E);
-    // rows were filled in increasing column order, so the position of column c inside row r is the
-    // number of earlier columns that touched r: walk columns again with per-row fill counters.
-    std::vector<int> fill((size_t)nrows, 0);
-    for (int c = 0; c < ncols; ++c) {
-        for (int p = g.col_ptr[(size_t)c]; p < g.col_ptr[(size_t)c + 1]; ++p) {
-            int r = g.col_row[(size_t)p];
-            g.col_edge[(size_t)p] = g.row_ptr[(size_t)r] + fill[(size_t)r]++;
-        }
-        g.max_col_deg = std::max(g.max_col_deg, g.col_ptr[(size_t)c + 1] - g.col_ptr[(size_t)c]);
-    }
     *out = std::move(g);
     return true;
 }

@@ -60,6 +60,24 @@ def test_product_encoder_matches_oracle(oracle):
         Encoder(cases[0][0]).encode([1, 0, 1], 5)       # wrong input length: reference panics
 
 
+def test_alist_parser_refuses_malformed_input_without_allocating(oracle):
+    """Error strings as reference src/sparse.rs:352-389 reports them; a header that promises a billion columns is
+    refused before anything is sized by it, and nothing escapes the C boundary as an exception."""
+    from ldpc_toolbox_b200 import Encoder
+    kat = "5 3\n2 4\n2 2 2 2 1\n2 4 4\n1 3\n2 3\n1 2\n2 3\n3\n1 3\n2 3 4\n1 2 4 5\n"
+    for text, why in [("", "enough elements"), ("5\n", "enough elements"), ("x 3\n", "ncols is not a number"),
+                      ("5 y\n", "nrows is not a number"), ("1073741823 3\n1 1\n", "expected number of lines"),
+                      ("4000000000 3\n", "too large"), ("5 3\n2 4\n", "expected number of lines"),
+                      (kat.replace("\n3\n", "\n4\n"), "out of range"), (kat.replace("\n3\n", "\n-1\n"), "not a number")]:
+        with pytest.raises(ValueError, match=why):
+            Encoder(text)
+    # zero padding, a repeated entry and a '+' sign are accepted and change nothing
+    padded = kat.replace("\n3\n", "\n3 0 0\n").replace("\n1 3\n2 3\n", "\n1 3 1\n+2 3\n", 1)
+    msg = np.array([1, 0], dtype=np.uint8)
+    assert (Encoder(padded).encode(msg, 5) == Encoder(kat).encode(msg, 5)).all()
+    assert (Encoder(padded).encode(msg, 5) == oracle.encoder(kat, "").encode(msg, 5)).all()
+
+
 def test_alist_generators_dimensions():
     from ldpc_toolbox_b200 import codes
     e = codes.dvbs2("R1_2")
