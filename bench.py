@@ -208,10 +208,15 @@ def run_ours(args):
 
     # ---- e2e ring: two pinned slots of half a launch each, filled with the timed batch's own LLRs
     half = frames // 2
-    h_llrs = [torch.empty((half, N), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-    h_out = [torch.zeros((half, K_INFO), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-    h_it = [torch.zeros((half,), dtype=torch.int32, pin_memory=True) for _ in range(2)]
-    for s in range(2):
+    ring = pinned_ring_slots(half * N * 4, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    try:
+        h_llrs = [torch.empty((half, N), dtype=torch.float32, pin_memory=True) for _ in range(ring)]
+    except RuntimeError:                                  # the host refused to pin two slots per rank: share one
+        ring = 1
+        h_llrs = [torch.empty((half, N), dtype=torch.float32, pin_memory=True)]
+    h_out = [torch.zeros((half, K_INFO), dtype=torch.uint8, pin_memory=True) for _ in range(ring)]
+    h_it = [torch.zeros((half,), dtype=torch.int32, pin_memory=True) for _ in range(ring)]
+    for s in range(ring):
         h_llrs[s].copy_(llrs[s * half:(s + 1) * half])
     torch.cuda.synchronize(dev)
 
@@ -238,7 +243,7 @@ def run_ours(args):
     def e2e_step():
         t = -1
         for i in range(submits):
-            s = i % 2
+            s = i % ring
             t = dec.submit_batch_ptr(h_llrs[s].data_ptr(), False, N, half, MAX_ITER, h_out[s].data_ptr(), K_INFO, K_INFO, h_it[s].data_ptr())
         dec.wait(t)
 
@@ -256,7 +261,7 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_frames = submits * half
     e2e_same = all(bool((h_out[s] == out_ref[s * half:(s + 1) * half]).all()) and bool((h_it[s] == it_ref[s * half:(s + 1) * half]).all())
-                   for s in range(2))
+                   for s in range(ring))
     e2e_gbps = K_INFO * e2e_frames * e2e_steps * world / e2e_s / 1e9
 
     value = K_INFO * frames * args.steps * world / (ms_total * 1e-3) / 1e9
@@ -275,7 +280,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": alg},
         "e2e": {"value": round(e2e_gbps, 4), "unit": "Gbit/s", "h2d_bytes_per_step": e2e_frames * N * 4,
                 "d2h_bytes_per_step": e2e_frames * (K_INFO + 4), "frames_per_step": e2e_frames, "submits_per_step": submits,
-                "frames_per_submit": half, "steps": e2e_steps, "pinned_ring_slots": 2,
+                "frames_per_submit": half, "steps": e2e_steps, "pinned_ring_slots": ring,
                 "identical_to_device_path": e2e_same},
         "waterfall": waterfall,
         "gpu_launches": 3 * args.steps,
@@ -292,6 +297,17 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def pinned_ring_slots(slot_bytes: int, ranks_on_host: int) -> int:
+    """Two pinned input slots per rank (19.6 GB each) unless that would take more than 60 % of the host memory that is
+    available right now (8 ranks need 315 GB): then every submit reads the same slot — the same bytes cross PCIe."""
+    try:
+        with open("/proc/meminfo") as f:
+            avail = next(int(l.split()[1]) * 1024 for l in f if l.startswith("MemAvailable:"))
+    except (OSError, StopIteration, ValueError):
+        return 2
+    return 2 if 2 * slot_bytes * ranks_on_host <= 0.6 * avail else 1
 
 
 def parity_check(sample, device: int):
