@@ -441,13 +441,22 @@ bool BerEngine::run(float ebn0_db, uint32_t max_iterations, uint64_t first_frame
     const int64_t t = submit(ebn0_db, max_iterations, first_frame, nframes, seed, bch_max_errors);
     if (t < 0) return false;
     Lane& ln = lanes_[t & 1];
-    // test hooks: the lane's buffers are intact until its next submit
-    if (dump_llrs) LDPC_CUDA_CHECK(cudaMemcpyAsync(dump_llrs, ln.d_llrs, nframes * (size_t)n_tx_ * sizeof(float), cudaMemcpyDeviceToHost, ln.stream));
-    if (dump_decoded) LDPC_CUDA_CHECK(cudaMemcpyAsync(dump_decoded, ln.d_decoded, nframes * (size_t)k_, cudaMemcpyDeviceToHost, ln.stream));
-    if (dump_iters) LDPC_CUDA_CHECK(cudaMemcpyAsync(dump_iters, ln.d_iters, nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, ln.stream));
-    if (dump_messages)
-        LDPC_CUDA_CHECK(cudaMemcpyAsync(dump_messages, ln.d_messages, nframes * ((size_t)(k_ + 31) / 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ln.stream));
-    LDPC_CUDA_CHECK(cudaStreamSynchronize(ln.stream));
+    // test hooks: the lane's buffers are intact until its next submit.  A failed copy must not leave the ticket in
+    // flight, so the lane is always waited for.
+    auto dump = [&](void* dst, const void* src, size_t bytes) {
+        return !dst || cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ln.stream) == cudaSuccess;
+    };
+    const bool dumped = dump(dump_llrs, ln.d_llrs, nframes * (size_t)n_tx_ * sizeof(float)) &&
+                        dump(dump_decoded, ln.d_decoded, nframes * (size_t)k_) &&
+                        dump(dump_iters, ln.d_iters, nframes * sizeof(int32_t)) &&
+                        dump(dump_messages, ln.d_messages, nframes * ((size_t)(k_ + 31) / 32) * sizeof(uint32_t)) &&
+                        cudaStreamSynchronize(ln.stream) == cudaSuccess;
+    if (!dumped) {
+        set_last_error(std::string("BER engine: dump copy failed: ") + cudaGetErrorString(cudaGetLastError()));
+        uint64_t scratch[kBerCounters] = {};
+        wait(t, scratch);
+        return false;
+    }
     return wait(t, counters);
 }
 
