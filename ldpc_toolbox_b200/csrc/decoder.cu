@@ -257,6 +257,9 @@ public:
         return ok;
     }
 
+    // waits for every host-path batch still in flight (no-op when there is none)
+    bool drain_tickets() { return tickets_.empty() || wait(tickets_.back().id); }
+
     // Test hook: decode_batch on one chunk that also returns every frame's posterior LLRs as f64 [nframes][n] — the
     // flooding decoder's output_llrs (flooding.rs:111-125) / the layered decoder's Qv — for the float decoders on the
     // K2 and K3q kernels.  Frames that pass the pre-check (0 iterations) have no posteriors (the reference's are stale).
@@ -271,6 +274,11 @@ public:
         DeviceScope scope(device_);
         if (!scope.ok) { set_last_error("cudaSetDevice failed"); return false; }
         if (nframes > plan_chunk_frames(nframes, 0)) { set_last_error("too many frames for one chunk"); return false; }
+        if (!drain_tickets()) return false;                 // this call uses the first lane's stream and workspace
+        struct HookReset {                                  // whatever happens below, the next decode must not dump
+            GpuDecoder* d;
+            ~HookReset() { d->dump_post_tiles_ = nullptr; d->dump_post_ = nullptr; }
+        } hook_reset{this};
         const size_t esz = is_f64 ? 8 : 4, n = (size_t)g_.n;
         DevBuf<uint8_t> d_in, d_out, d_post_tiles;
         DevBuf<int32_t> d_it;
@@ -290,8 +298,6 @@ public:
         LDPC_CUDA_CHECK(cudaMemcpyAsync(d_in.p, llrs, nframes * llrs_len * esz, cudaMemcpyHostToDevice, stream_));
         const bool ok = run_chunk(ws_[0], d_in.p, is_f64, llrs_len, nframes, max_iterations, d_out.p, out_len, out_len, d_it.p, stream_);
         void* tiles_ptr = dump_post_tiles_;
-        dump_post_tiles_ = nullptr;
-        dump_post_ = nullptr;
         if (!ok) return false;
         if (tiles_ptr && !launch_emit_posteriors(tiles_ptr, impl_.dtype == Dtype::F64, g_.n, nframes, d_post.p, stream_)) return false;
         if (out_len) LDPC_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride, d_out.p, out_len, out_len, nframes, cudaMemcpyDeviceToHost, stream_));
@@ -315,6 +321,7 @@ public:
         if (nframes == 0) return true;
         DeviceScope scope(device_);
         if (!scope.ok) { set_last_error("cudaSetDevice failed"); return false; }
+        if (!drain_tickets()) return false;                 // host-path batches in flight own the same workspaces
         const size_t esz = is_f64 ? 8 : 4;
         const size_t chunk_frames = plan_chunk_frames(nframes, 0);
         for (size_t f0 = 0; f0 < nframes; f0 += chunk_frames) {
