@@ -425,3 +425,27 @@ int main(int argc, char **argv) {
         assert run.returncode == 0 and run.stdout.strip() == "0"
     else:
         assert run.returncode == 3 and run.stdout.strip() == "NULL"
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside the GPU arm): one JSON line with the contract's
+    keys from rank 0, nothing and exit code 0 from any other rank; only the checker's library is involved."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-seconds", "0.5"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "Gbit/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"] and line["gpu_launches"] == 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert abs(line["ms_per_step"] - 1e3 * line["run"]["frames_per_step"] / line["run"]["frames_per_s"]) < 0.05 * line["ms_per_step"]
+    import bench
+    assert line["config"] == bench.CONFIG and line["metric"] == bench.METRIC      # identical in both arms
+    r1 = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), timeout=60)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
